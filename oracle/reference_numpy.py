@@ -1,0 +1,213 @@
+"""TEST INFRASTRUCTURE — CPU oracle for the global statistical colour-transfer path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product path (color-transfer_b200/) never does and
+fails loudly when its CUDA library is missing.
+
+A numpy restatement of the reference's hot path, written stage by stage so that
+every intermediate the CUDA kernels must reproduce bit-for-bit (rotations,
+projected ranges, bin edges, integer counts, CDFs, inverse-CDF tables, bin
+indices) can be inspected:
+
+* Reinhard Lab mean/std matching      ref: methods/linear.py:8-42
+* Xiao correlated colour space        ref: methods/linear.py:45-82
+* Pitie Monge-Kantorovitch            ref: methods/linear.py:85-124
+* Pitie iterative distribution transfer  ref: methods/iterative.py:8-59
+
+Pinning: ``oracle/gen_golden.py`` executes the UNMODIFIED reference files
+(loaded by path from /root/reference, see oracle/load_reference.py) on seeded
+inputs and on the 0964 stereo pair, checks that this restatement returns
+bit-identical arrays for Xiao / MKL / IDT, and writes the golden vectors under
+tests/golden/.  The reference itself has no tests or golden vectors
+(SURVEY.md section 4), so those generated vectors are the pin.  The Lab
+conversion inside the Reinhard transfer is the one part that cannot be pinned
+(scikit-image is absent; see oracle/skimage_color.py: "parity unpinned").
+"""
+
+import numpy as np
+import scipy.linalg
+import scipy.stats
+
+from . import skimage_color
+
+# --------------------------------------------------------------------------- linear
+
+
+def lab_statistics(img):
+    """Per-channel Lab mean and population std of one RGB image.
+    ref: methods/linear.py:25-36 (np.mean / np.std over axis 0, ddof=0)."""
+    lab = skimage_color.rgb2lab(img).reshape(-1, 3)
+    return np.mean(lab, axis=0), np.std(lab, axis=0)
+
+
+def color_transfer_between_images(target, reference):
+    """Reinhard et al. 2001.  ref: methods/linear.py:8-42."""
+    t_lab = skimage_color.rgb2lab(target)
+    r_lab = skimage_color.rgb2lab(reference)
+    hw3 = t_lab.shape
+    t = t_lab.reshape(-1, 3)
+    r = r_lab.reshape(-1, 3)
+    mu_t, mu_r = np.mean(t, axis=0), np.mean(r, axis=0)
+    sd_t, sd_r = np.std(t, axis=0), np.std(r, axis=0)
+    moved = (t - mu_t) * sd_r / sd_t + mu_r              # :38
+    return skimage_color.lab2rgb(moved.reshape(hw3))     # :40 (clips to [0,1])
+
+
+def mean_and_cov(img):
+    """np.mean(axis=0) and np.cov(X.T) (ddof=1) of the flattened pixels.
+    ref: methods/linear.py:64-67 and :103-106."""
+    x = np.asarray(img).reshape(-1, 3)
+    return np.mean(x, axis=0), np.cov(x.T)
+
+
+def ccs_matrix(cov_t, cov_r, signs=None):
+    """T of Xiao & Ma: U_t S_t^-1/2 S_r^1/2 U_r^-1.  ref: methods/linear.py:69-78.
+    ``signs`` (length 3, +-1) optionally flips the columns of U_r; it exists only so
+    tests can quantify the LAPACK sign ambiguity."""
+    u_t, s_t, _ = np.linalg.svd(cov_t)
+    u_r, s_r, _ = np.linalg.svd(cov_r)
+    if signs is not None:
+        u_r = u_r * np.asarray(signs, dtype=np.float64)[None, :]
+    return u_t @ np.diag(1 / np.sqrt(s_t)) @ np.diag(np.sqrt(s_r)) @ np.linalg.inv(u_r)
+
+
+def color_transfer_in_correlated_color_space(target, reference):
+    """Xiao & Ma 2006.  ref: methods/linear.py:45-82 (applies ``@ T.T``)."""
+    hw3 = target.shape
+    t = target.reshape(-1, 3)
+    r = reference.reshape(-1, 3)
+    mu_t, cov_t = mean_and_cov(t)
+    mu_r, cov_r = mean_and_cov(r)
+    T = ccs_matrix(cov_t, cov_r)
+    return ((t - mu_t) @ T.T + mu_r).reshape(hw3)
+
+
+def mkl_matrix(cov_t, cov_r, decomposition="MK"):
+    """The three closed forms of Pitie & Kokaram 2007.  ref: methods/linear.py:108-120."""
+    if decomposition == "cholesky":
+        return np.linalg.cholesky(cov_r) @ np.linalg.inv(np.linalg.cholesky(cov_t))
+    if decomposition == "sqrt":
+        return scipy.linalg.sqrtm(cov_r) @ np.linalg.inv(scipy.linalg.sqrtm(cov_t))
+    if decomposition == "MK":
+        root_t = scipy.linalg.sqrtm(cov_t)
+        inv_root_t = np.linalg.inv(root_t)
+        return inv_root_t @ scipy.linalg.sqrtm(root_t @ cov_r @ root_t) @ inv_root_t
+    raise ValueError("Unknown decomposition, use either 'cholesky', 'sqrt', or 'MK'")
+
+
+def monge_kantorovitch_color_transfer(target, reference, decomposition="MK"):
+    """Pitie & Kokaram 2007.  ref: methods/linear.py:85-124 (applies ``@ T``)."""
+    hw3 = target.shape
+    t = target.reshape(-1, 3)
+    r = reference.reshape(-1, 3)
+    mu_t, cov_t = mean_and_cov(t)
+    mu_r, cov_r = mean_and_cov(r)
+    T = mkl_matrix(cov_t, cov_r, decomposition)
+    return ((t - mu_t) @ T + mu_r).reshape(hw3)
+
+
+# --------------------------------------------------------------------------- IDT stages
+
+
+def draw_rotation(n_dims=3):
+    """One Haar-random rotation from the GLOBAL numpy RNG.  ref: methods/iterative.py:32."""
+    return scipy.stats.special_ortho_group.rvs(n_dims)
+
+
+def project(rot, pixels):
+    """rot @ pixels.T -> [3, N] float64.  ref: methods/iterative.py:34-35."""
+    return rot @ pixels.T
+
+
+def axis_range(p_t, p_r):
+    """Shared range of one projected axis.  ref: methods/iterative.py:39-40."""
+    return min(p_t.min(), p_r.min()), max(p_t.max(), p_r.max())
+
+
+def axis_histograms(p_t, p_r, lo, hi, bins):
+    """Integer counts of both images on the shared uniform grid.
+    ref: methods/iterative.py:42-43."""
+    c_t, edges = np.histogram(p_t, bins=bins, range=[lo, hi])
+    c_r, _ = np.histogram(p_r, bins=bins, range=[lo, hi])
+    return c_t, c_r, edges
+
+
+def cdf(counts):
+    """Normalised cumulative histogram.  ref: methods/iterative.py:45-49."""
+    c = counts.cumsum().astype(float)
+    c /= c[-1]
+    return c
+
+
+def inverse_cdf_lut(cdf_t, cdf_r, edges):
+    """f[i] = value whose reference-CDF equals the target-CDF at the right edge of
+    bin i.  ref: methods/iterative.py:51."""
+    return np.interp(cdf_t, cdf_r, edges[1:])
+
+
+def remap_axis(p_t, edges, lut, bins):
+    """Per-sample lookup + linear interpolation; values left of edges[1] map to 0
+    (the reference's first-bin behaviour).  ref: methods/iterative.py:53."""
+    return np.interp(p_t, edges[1:], lut, left=0, right=bins)
+
+
+def bin_index(p, edges):
+    """The bin np.histogram puts each sample in (unique k with
+    edges[k] <= x < edges[k+1], last bin closed).  Restates the uniform fast path of
+    numpy/lib/_histograms_impl.py (estimate, clamp, -1/+1 correction)."""
+    bins = len(edges) - 1
+    lo, hi = edges[0], edges[-1]
+    k = (((p - lo) / (hi - lo)) * bins).astype(np.intp)
+    k[k == bins] -= 1
+    k[p < edges[k]] -= 1
+    k[(p >= edges[k + 1]) & (k != bins - 1)] += 1
+    return k
+
+
+def back_rotate(rot, moved, projected, state):
+    """ref: methods/iterative.py:55."""
+    return np.linalg.solve(rot, moved - projected).T + state
+
+
+def idt_iteration(state, reference, rot, bins, moved_dtype):
+    """One full iteration; returns the new state and a dict of every intermediate."""
+    p_t = project(rot, state)
+    p_r = project(rot, reference)
+    moved = np.empty(p_t.shape, dtype=moved_dtype)      # np.empty_like(target.T), :36
+    trace = {"rot": rot, "lo": [], "hi": [], "edges": [], "counts_t": [], "counts_r": [],
+             "lut": [], "proj_t": p_t}
+    for j in range(p_t.shape[0]):
+        lo, hi = axis_range(p_t[j], p_r[j])
+        c_t, c_r, edges = axis_histograms(p_t[j], p_r[j], lo, hi, bins)
+        lut = inverse_cdf_lut(cdf(c_t), cdf(c_r), edges)
+        moved[j] = remap_axis(p_t[j], edges, lut, bins)
+        for key, val in (("lo", lo), ("hi", hi), ("edges", edges), ("counts_t", c_t),
+                         ("counts_r", c_r), ("lut", lut)):
+            trace[key].append(val)
+    new_state = back_rotate(rot, moved, p_t, state)
+    for key in ("lo", "hi", "edges", "counts_t", "counts_r", "lut"):
+        trace[key] = np.asarray(trace[key])
+    trace["moved"] = moved
+    trace["state"] = new_state
+    return new_state, trace
+
+
+def idt_instrumented(target, reference, bins=255, n_iter=4, rotations=None):
+    """IDT that also returns the per-iteration traces.  ``rotations`` (n_iter x 3 x 3)
+    replaces the RNG draws when given (used when the matrices were pre-drawn)."""
+    hw3 = target.shape
+    state = target.reshape(-1, 3)
+    ref = reference.reshape(-1, 3)
+    traces = []
+    for it in range(n_iter):
+        rot = draw_rotation(hw3[-1]) if rotations is None else np.asarray(rotations[it])
+        # the reference allocates the remapped values with the dtype of the CURRENT
+        # state: float32 in iteration 0 for float32 input, float64 afterwards.
+        state, tr = idt_iteration(state, ref, rot, bins, state.dtype)
+        traces.append(tr)
+    return state.reshape(hw3), traces
+
+
+def iterative_distribution_transfer(target, reference, bins=255, n_iter=4):
+    """Pitie, Kokaram & Dahyot 2007.  ref: methods/iterative.py:8-59."""
+    return idt_instrumented(target, reference, bins, n_iter)[0]
