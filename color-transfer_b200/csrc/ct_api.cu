@@ -1,0 +1,480 @@
+// C ABI of libct_b200.so (include/ct_b200.h): handle management, argument checking, the fused
+// device drivers and the host-buffer pipelines.
+#include <new>
+#include <vector>
+
+#include "ct_context.h"
+
+namespace ct {
+
+int check_batch(ct_context *h, const ct_batch *b, const char *name) {
+    if (!b) return fail(h, CT_E_INVALID, "%s is NULL", name);
+    if (!b->data) return fail(h, CT_E_INVALID, "%s.data is NULL", name);
+    if (b->npix <= 0) return fail(h, CT_E_INVALID, "%s.npix must be positive (got %lld)", name, (long long)b->npix);
+    if (b->count <= 0) return fail(h, CT_E_INVALID, "%s.count must be positive", name);
+    if (b->dtype != CT_F32 && b->dtype != CT_F64) return fail(h, CT_E_INVALID, "%s.dtype unknown", name);
+    if (b->layout != CT_HWC && b->layout != CT_CHW) return fail(h, CT_E_INVALID, "%s.layout unknown", name);
+    if (b->count > 65535) return fail(h, CT_E_UNSUPPORTED, "%s.count above 65535 pairs per call", name);
+    if (((uintptr_t)b->data) % elem_size(b->dtype)) return fail(h, CT_E_INVALID, "%s.data is not element aligned", name);
+    return CT_OK;
+}
+
+template <typename T>
+static int grow(ct_context *h, T **ptr, size_t *have, size_t want, bool zero) {
+    if (*have >= want && *ptr) return CT_OK;
+    if (*ptr) {
+        CT_CUDA(h, cudaStreamSynchronize(h->stream));
+        CT_CUDA(h, cudaFree(*ptr));
+        *ptr = nullptr;
+        *have = 0;
+    }
+    size_t n = want + want / 4;
+    void *p = nullptr;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
+        n = want;
+        if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess)
+            return fail(h, CT_E_NOMEM, "cudaMalloc of %zu bytes failed", n * sizeof(T));
+    }
+    if (zero) CT_CUDA(h, cudaMemsetAsync(p, 0, n * sizeof(T), h->stream));
+    *ptr = static_cast<T *>(p);
+    *have = n;
+    return CT_OK;
+}
+
+int ensure_partials(ct_context *h, size_t doubles) { return grow(h, &h->partials, &h->partials_doubles, doubles, false); }
+
+int ensure_scratch(ct_context *h, int pairs) {
+    if (pairs <= h->scratch_pairs) return CT_OK;
+    int cap = h->scratch_pairs * 2;
+    if (cap < pairs) cap = pairs;
+    if (cap < 64) cap = 64;
+    size_t have_t = 0, have_x = 0, have_s = 0, have_st = 0;
+    if (h->scratch_pairs) CT_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->tickets); cudaFree(h->xform); cudaFree(h->sums); cudaFree(h->status);
+    h->tickets = nullptr; h->xform = nullptr; h->sums = nullptr; h->status = nullptr;
+    h->scratch_pairs = 0;
+    CT_TRY(grow(h, &h->tickets, &have_t, (size_t)cap, true));
+    CT_TRY(grow(h, &h->xform, &have_x, (size_t)cap * CT_XFORM_DOUBLES, false));
+    CT_TRY(grow(h, &h->sums, &have_s, (size_t)cap * 2 * CT_MOMENT_DOUBLES, false));
+    CT_TRY(grow(h, &h->status, &have_st, (size_t)cap, true));
+    if (h->host_status) cudaFreeHost(h->host_status);
+    h->host_status = nullptr;
+    CT_CUDA(h, cudaMallocHost(&h->host_status, sizeof(int) * (size_t)cap));
+    h->scratch_pairs = cap;
+    return CT_OK;
+}
+
+int ensure_ws(ct_context *h, size_t bytes) {
+    unsigned char *p = static_cast<unsigned char *>(h->ws);
+    CT_TRY(grow(h, &p, &h->ws_bytes, bytes, false));
+    h->ws = p;
+    return CT_OK;
+}
+int ensure_stage(ct_context *h, size_t bytes) {
+    unsigned char *p = static_cast<unsigned char *>(h->stage);
+    CT_TRY(grow(h, &p, &h->stage_bytes, bytes, false));
+    h->stage = p;
+    return CT_OK;
+}
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct Carver {
+    unsigned char *base;
+    size_t off = 0;
+    explicit Carver(void *b) : base(static_cast<unsigned char *>(b)) {}
+    template <typename T> T *take(size_t n) {
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off = align_up(off + n * sizeof(T));
+        return p;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// IDT fused driver
+// ---------------------------------------------------------------------------------------------
+struct IdtLayout {
+    double *state;
+    int64_t plane, state_stride;
+    int64_t *keys;
+    uint64_t *counts;
+    double *lut;
+    int32_t *status;
+    size_t bytes;
+};
+
+static IdtLayout idt_layout(void *base, int64_t npix, int count, int bins, int n_iter) {
+    IdtLayout L{};
+    Carver c(base);
+    L.plane = (npix + 1) / 2 * 2;
+    L.state_stride = 3 * L.plane;
+    L.state = n_iter >= 2 ? c.take<double>((size_t)count * L.state_stride) : nullptr;
+    L.keys = c.take<int64_t>((size_t)count * (n_iter + 1) * CT_IDT_KEYS);
+    L.counts = c.take<uint64_t>((size_t)count * 6 * bins);
+    L.lut = c.take<double>((size_t)count * CT_IDT_LUT_DOUBLES(bins));
+    L.status = c.take<int32_t>((size_t)count);
+    L.bytes = c.off;
+    return L;
+}
+
+static int idt_run(ct_context *h, const ct_batch *target, const ct_batch *reference, const ct_batch *out,
+                   const double *rotations, int bins, int n_iter, void *workspace, size_t workspace_bytes,
+                   const ct_idt_trace *trace, int32_t *status) {
+    CT_TRY(check_batch(h, target, "target"));
+    CT_TRY(check_batch(h, reference, "reference"));
+    CT_TRY(check_batch(h, out, "out"));
+    if (!rotations) return fail(h, CT_E_INVALID, "rotations is NULL");
+    if (n_iter < 1) return fail(h, CT_E_INVALID, "n_iter must be >= 1 (n_iter = 0 is a host-side copy)");
+    if (bins < 1) return fail(h, CT_E_INVALID, "bins must be >= 1");
+    if (bins > CT_IDT_MAX_BINS) return fail(h, CT_E_UNSUPPORTED, "bins=%d exceeds CT_IDT_MAX_BINS=%d", bins, CT_IDT_MAX_BINS);
+    if (reference->count != target->count || out->count != target->count) return fail(h, CT_E_INVALID, "batch counts differ");
+    if (out->npix != target->npix) return fail(h, CT_E_INVALID, "out.npix != target.npix");
+    if (out->dtype != CT_F64 || out->layout != CT_HWC) return fail(h, CT_E_INVALID, "IDT output must be float64 CT_HWC");
+    const int B = target->count;
+    const size_t need = idt_layout(nullptr, target->npix, B, bins, n_iter).bytes;
+    if (!workspace) {
+        CT_TRY(ensure_ws(h, need));
+        workspace = h->ws;
+    } else if (workspace_bytes < need) {
+        return fail(h, CT_E_NOMEM, "IDT workspace too small: %zu < %zu", workspace_bytes, need);
+    }
+    const IdtLayout L = idt_layout(workspace, target->npix, B, bins, n_iter);
+    int32_t *st = status ? status : L.status;
+    CT_CUDA(h, cudaMemsetAsync(L.counts, 0, sizeof(uint64_t) * (size_t)B * 6 * bins, h->stream));
+    CT_CUDA(h, cudaMemsetAsync(st, 0, sizeof(int32_t) * (size_t)B, h->stream));
+    const int64_t keys_stride = (int64_t)(n_iter + 1) * CT_IDT_KEYS, rot_stride = (int64_t)n_iter * 9;
+    CT_TRY(launch_keys_init(h, L.keys, (int64_t)B * keys_stride));
+    CT_TRY(launch_ranges(h, target, rotations, rot_stride, L.keys, keys_stride, st));
+    CT_TRY(launch_ranges(h, reference, rotations, rot_stride, L.keys, keys_stride, st));
+
+    ct_batch state{};
+    state.data = L.state;
+    state.npix = target->npix;
+    state.image_stride = L.state_stride;
+    state.plane_stride = L.plane;
+    state.count = B;
+    state.dtype = CT_F64;
+    state.layout = CT_CHW;
+    for (int it = 0; it < n_iter; ++it) {
+        const bool last = it == n_iter - 1;
+        ct_idt_stage s{};
+        s.target = it == 0 ? target : &state;
+        s.reference = reference;
+        s.rot = rotations + it * 9;
+        s.rot_next = last ? nullptr : rotations + (it + 1) * 9;
+        s.rot_stride = rot_stride;
+        s.keys = L.keys + it * CT_IDT_KEYS;
+        s.keys_next = last ? nullptr : L.keys + (it + 1) * CT_IDT_KEYS;
+        s.keys_stride = keys_stride;
+        s.counts = L.counts;
+        s.lut = L.lut;
+        s.status = st;
+        s.bins = bins;
+        CT_TRY(launch_hist(h, &s, 1, trace, it, n_iter));
+        CT_TRY(launch_remap(h, &s, last ? out : &state, it == 0 && target->dtype == CT_F32));
+    }
+    return CT_OK;
+}
+
+}  // namespace ct
+
+using namespace ct;
+
+// =============================================================================================
+extern "C" {
+
+int ct_abi_version(void) { return CT_ABI_VERSION; }
+
+int ct_create(int device, ct_handle *out) {
+    if (!out) return CT_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return CT_E_CUDA;
+    ct_context *h = new (std::nothrow) ct_context();
+    if (!h) return CT_E_NOMEM;
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return CT_E_CUDA; }
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return CT_E_CUDA;
+    }
+    *out = h;
+    return CT_OK;
+}
+
+void ct_destroy(ct_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->partials);
+    cudaFree(h->tickets);
+    cudaFree(h->xform);
+    cudaFree(h->sums);
+    cudaFree(h->status);
+    cudaFree(h->ws);
+    cudaFree(h->stage);
+    if (h->host_status) cudaFreeHost(h->host_status);
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
+    delete h;
+}
+
+const char *ct_last_error(ct_handle h) { return h ? h->err : "null handle"; }
+
+int ct_set_stream(ct_handle h, void *cuda_stream) {
+    if (!h) return CT_E_INVALID;
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return CT_OK;
+}
+
+int ct_synchronize(ct_handle h) {
+    if (!h) return CT_E_INVALID;
+    CT_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CT_OK;
+}
+
+int ct_sm_count(ct_handle h) { return h ? h->sm_count : 0; }
+int64_t ct_launch_count(ct_handle h) { return h ? h->launches : 0; }
+
+#define CT_ENTER(h)                             \
+    if (!(h)) return CT_E_INVALID;              \
+    (h)->err[0] = 0;                            \
+    CT_CUDA((h), cudaSetDevice((h)->device))
+
+// ------------------------------------------------------------------ linear
+int ct_moments(ct_handle h, const ct_batch *images, int lab, double *sums) {
+    CT_ENTER(h);
+    return launch_moments(h, images, nullptr, lab, sums, -1, nullptr, nullptr);
+}
+
+int ct_linear_solve(ct_handle h, int method, const double *sums_t, const double *sums_r, int count,
+                    double *xform, int *status) {
+    CT_ENTER(h);
+    return launch_solve(h, method, sums_t, sums_r, CT_MOMENT_DOUBLES, count, xform, status);
+}
+
+int ct_linear_apply(ct_handle h, int method, const ct_batch *target, const double *xform, const ct_batch *out) {
+    CT_ENTER(h);
+    if (method < CT_REINHARD || method > CT_MKL_CHOLESKY) return fail(h, CT_E_INVALID, "unknown method %d", method);
+    return launch_apply(h, method, target, xform, out);
+}
+
+int ct_linear_transfer(ct_handle h, int method, const ct_batch *target, const ct_batch *reference,
+                       const ct_batch *out, double *xform, int *status) {
+    CT_ENTER(h);
+    if (method < CT_REINHARD || method > CT_MKL_CHOLESKY) return fail(h, CT_E_INVALID, "unknown method %d", method);
+    CT_TRY(check_batch(h, target, "target"));
+    CT_TRY(ensure_scratch(h, target->count));
+    if (!xform) xform = h->xform;
+    if (!status) status = h->status;
+    CT_TRY(launch_moments(h, target, reference, method == CT_REINHARD, h->sums, method, xform, status));
+    return launch_apply(h, method, target, xform, out);
+}
+
+}  // extern "C"
+
+// Host pipeline shared by the two *_host entry points: per pair H2D on copy_in, kernels on the
+// handle's stream, D2H on copy_out, two slots in flight.
+namespace {
+constexpr int kSlots = 2;
+struct Pipeline {
+    cudaEvent_t in_ready[kSlots], done[kSlots], out_free[kSlots];
+    bool ok = false;
+    int init() {
+        for (int i = 0; i < kSlots; ++i) {
+            if (cudaEventCreateWithFlags(&in_ready[i], cudaEventDisableTiming) != cudaSuccess) return -1;
+            if (cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess) return -1;
+            if (cudaEventCreateWithFlags(&out_free[i], cudaEventDisableTiming) != cudaSuccess) return -1;
+        }
+        ok = true;
+        return 0;
+    }
+    ~Pipeline() {
+        if (!ok) return;
+        for (int i = 0; i < kSlots; ++i) {
+            cudaEventDestroy(in_ready[i]);
+            cudaEventDestroy(done[i]);
+            cudaEventDestroy(out_free[i]);
+        }
+    }
+};
+
+ct_batch single(const ct_batch *b, void *data) {
+    ct_batch s = *b;
+    s.data = data;
+    s.count = 1;
+    s.image_stride = 0;
+    return s;
+}
+void *host_image(const ct_batch *b, int i) {
+    return static_cast<unsigned char *>(b->data) + (size_t)i * (size_t)b->image_stride * elem_size(b->dtype);
+}
+size_t image_bytes(const ct_batch *b) {
+    // CHW with padded planes is copied as one block including the padding
+    const int64_t elems = b->layout == CT_CHW ? 2 * plane_of(b) + b->npix : 3 * b->npix;
+    return (size_t)elems * elem_size(b->dtype);
+}
+
+template <typename Launch>
+int run_host_pipeline(ct_context *h, const ct_batch *target, const ct_batch *reference, const ct_batch *out,
+                      size_t extra_ws, Launch &&launch) {
+    const int B = target->count;
+    const size_t tb = align_up(image_bytes(target)), rb = align_up(image_bytes(reference)), ob = align_up(image_bytes(out));
+    const int slots = B > 1 ? kSlots : 1;
+    CT_TRY(ensure_stage(h, (tb + rb + ob) * slots + extra_ws));
+    Pipeline pl;
+    if (pl.init() != 0) return fail(h, CT_E_CUDA, "event creation failed");
+    unsigned char *base = static_cast<unsigned char *>(h->stage);
+    for (int b = 0; b < B; ++b) {
+        const int s = b % slots;
+        unsigned char *dt = base + (size_t)s * (tb + rb + ob), *dr = dt + tb, *dout = dr + rb;
+        if (b >= slots) CT_CUDA(h, cudaStreamWaitEvent(h->copy_in, pl.done[s], 0));
+        CT_CUDA(h, cudaMemcpyAsync(dt, host_image(target, b), image_bytes(target), cudaMemcpyHostToDevice, h->copy_in));
+        CT_CUDA(h, cudaMemcpyAsync(dr, host_image(reference, b), image_bytes(reference), cudaMemcpyHostToDevice, h->copy_in));
+        CT_CUDA(h, cudaEventRecord(pl.in_ready[s], h->copy_in));
+        CT_CUDA(h, cudaStreamWaitEvent(h->stream, pl.in_ready[s], 0));
+        if (b >= slots) CT_CUDA(h, cudaStreamWaitEvent(h->stream, pl.out_free[s], 0));
+        const ct_batch t1 = single(target, dt), r1 = single(reference, dr), o1 = single(out, dout);
+        CT_TRY(launch(b, &t1, &r1, &o1));
+        CT_CUDA(h, cudaEventRecord(pl.done[s], h->stream));
+        CT_CUDA(h, cudaStreamWaitEvent(h->copy_out, pl.done[s], 0));
+        CT_CUDA(h, cudaMemcpyAsync(host_image(out, b), dout, image_bytes(out), cudaMemcpyDeviceToHost, h->copy_out));
+        CT_CUDA(h, cudaEventRecord(pl.out_free[s], h->copy_out));
+    }
+    CT_CUDA(h, cudaStreamSynchronize(h->copy_out));
+    CT_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CT_OK;
+}
+
+int first_bad_status(ct_context *h, const int *dev_status, int B) {
+    if (cudaMemcpyAsync(h->host_status, dev_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+        cudaStreamSynchronize(h->stream) != cudaSuccess)
+        return fail(h, CT_E_CUDA, "status read-back failed");
+    for (int b = 0; b < B; ++b)
+        if (h->host_status[b] != CT_OK) {
+            const int st = h->host_status[b];
+            const char *what = st == CT_E_NONFINITE ? "projected range is not finite"
+                               : st == CT_E_NOT_PD  ? "Matrix is not positive definite"
+                               : st == CT_E_SINGULAR ? "Singular matrix"
+                                                     : "kernel reported an error";
+            return fail(h, st, "pair %d: %s", b, what);
+        }
+    return CT_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ct_linear_transfer_host(ct_handle h, int method, const ct_batch *target, const ct_batch *reference,
+                            const ct_batch *out) {
+    CT_ENTER(h);
+    if (method < CT_REINHARD || method > CT_MKL_CHOLESKY) return fail(h, CT_E_INVALID, "unknown method %d", method);
+    CT_TRY(check_batch(h, target, "target"));
+    CT_TRY(check_batch(h, reference, "reference"));
+    CT_TRY(check_batch(h, out, "out"));
+    if (reference->count != target->count || out->count != target->count) return fail(h, CT_E_INVALID, "batch counts differ");
+    CT_TRY(ensure_scratch(h, target->count));
+    CT_CUDA(h, cudaMemsetAsync(h->status, 0, sizeof(int) * (size_t)target->count, h->stream));
+    CT_TRY(run_host_pipeline(h, target, reference, out, 0,
+                             [&](int b, const ct_batch *t, const ct_batch *r, const ct_batch *o) {
+                                 CT_TRY(launch_moments(h, t, r, method == CT_REINHARD, h->sums + (size_t)b * 2 * CT_MOMENT_DOUBLES,
+                                                       method, h->xform + (size_t)b * CT_XFORM_DOUBLES, h->status + b));
+                                 return launch_apply(h, method, t, h->xform + (size_t)b * CT_XFORM_DOUBLES, o);
+                             }));
+    return first_bad_status(h, h->status, target->count);
+}
+
+// ------------------------------------------------------------------ IDT
+int ct_idt_keys_init(ct_handle h, int64_t *keys, int64_t n) {
+    CT_ENTER(h);
+    return launch_keys_init(h, keys, n);
+}
+int ct_idt_ranges(ct_handle h, const ct_batch *images, const double *rot, int64_t rot_stride, int64_t *keys,
+                  int64_t keys_stride, int32_t *status) {
+    CT_ENTER(h);
+    return launch_ranges(h, images, rot, rot_stride, keys, keys_stride, status);
+}
+int ct_idt_hist(ct_handle h, const ct_idt_stage *s, int fuse_lut) {
+    CT_ENTER(h);
+    return launch_hist(h, s, fuse_lut, nullptr, 0, 1);
+}
+int ct_idt_lut(ct_handle h, const ct_idt_stage *s, int keep_counts) {
+    CT_ENTER(h);
+    return launch_lut(h, s, keep_counts, nullptr, 0, 1);
+}
+int ct_idt_remap(ct_handle h, const ct_idt_stage *s, const ct_batch *dst, int round_f32) {
+    CT_ENTER(h);
+    return launch_remap(h, s, dst, round_f32);
+}
+
+size_t ct_idt_workspace_bytes(int64_t npix_target, int32_t count, int32_t bins, int32_t n_iter) {
+    if (npix_target <= 0 || count <= 0 || bins <= 0 || n_iter <= 0) return 0;
+    return idt_layout(nullptr, npix_target, count, bins, n_iter).bytes;
+}
+
+int ct_idt_transfer(ct_handle h, const ct_batch *target, const ct_batch *reference, const ct_batch *out,
+                    const double *rotations, int32_t bins, int32_t n_iter, void *workspace,
+                    size_t workspace_bytes, const ct_idt_trace *trace, int32_t *status) {
+    CT_ENTER(h);
+    return idt_run(h, target, reference, out, rotations, bins, n_iter, workspace, workspace_bytes, trace, status);
+}
+
+int ct_idt_transfer_host(ct_handle h, const ct_batch *target, const ct_batch *reference, const ct_batch *out,
+                         const double *rotations, int32_t bins, int32_t n_iter, const ct_idt_trace *trace) {
+    CT_ENTER(h);
+    CT_TRY(check_batch(h, target, "target"));
+    CT_TRY(check_batch(h, reference, "reference"));
+    CT_TRY(check_batch(h, out, "out"));
+    if (!rotations) return fail(h, CT_E_INVALID, "rotations is NULL");
+    if (n_iter < 1 || bins < 1) return fail(h, CT_E_INVALID, "n_iter and bins must be >= 1");
+    if (bins > CT_IDT_MAX_BINS) return fail(h, CT_E_UNSUPPORTED, "bins=%d exceeds CT_IDT_MAX_BINS=%d", bins, CT_IDT_MAX_BINS);
+    if (reference->count != target->count || out->count != target->count) return fail(h, CT_E_INVALID, "batch counts differ");
+    const int B = target->count;
+    CT_TRY(ensure_scratch(h, B));
+    // device-side small buffers: rotations, per-pair status, optional trace
+    const size_t per_axis = (size_t)B * n_iter * 3;
+    Carver probe(nullptr);
+    probe.take<double>((size_t)B * n_iter * 9);
+    if (trace) {
+        probe.take<double>(per_axis); probe.take<double>(per_axis);
+        probe.take<int64_t>(per_axis * bins); probe.take<int64_t>(per_axis * bins); probe.take<double>(per_axis * bins);
+    }
+    const size_t small_bytes = probe.off;
+    const size_t idt_ws = idt_layout(nullptr, target->npix, 1, bins, n_iter).bytes;
+    CT_TRY(ensure_ws(h, small_bytes + idt_ws));
+    Carver c(h->ws);
+    double *d_rot = c.take<double>((size_t)B * n_iter * 9);
+    ct_idt_trace dtr{};
+    if (trace) {
+        dtr.lo = c.take<double>(per_axis); dtr.hi = c.take<double>(per_axis);
+        dtr.counts_t = c.take<int64_t>(per_axis * bins); dtr.counts_r = c.take<int64_t>(per_axis * bins);
+        dtr.lut = c.take<double>(per_axis * bins);
+    }
+    void *idt_base = static_cast<unsigned char *>(h->ws) + small_bytes;
+    CT_CUDA(h, cudaMemcpyAsync(d_rot, rotations, sizeof(double) * (size_t)B * n_iter * 9, cudaMemcpyHostToDevice, h->stream));
+    CT_CUDA(h, cudaMemsetAsync(h->status, 0, sizeof(int) * (size_t)B, h->stream));
+    CT_TRY(run_host_pipeline(h, target, reference, out, 0,
+                             [&](int b, const ct_batch *t, const ct_batch *r, const ct_batch *o) {
+                                 ct_idt_trace tb = dtr;
+                                 if (trace) {
+                                     const size_t o3 = (size_t)b * n_iter * 3;
+                                     tb.lo += o3; tb.hi += o3;
+                                     tb.counts_t += o3 * bins; tb.counts_r += o3 * bins; tb.lut += o3 * bins;
+                                 }
+                                 return idt_run(h, t, r, o, d_rot + (size_t)b * n_iter * 9, bins, n_iter, idt_base, idt_ws,
+                                                trace ? &tb : nullptr, h->status + b);
+                             }));
+    if (trace) {
+        if (trace->lo) CT_CUDA(h, cudaMemcpyAsync(trace->lo, dtr.lo, sizeof(double) * per_axis, cudaMemcpyDeviceToHost, h->stream));
+        if (trace->hi) CT_CUDA(h, cudaMemcpyAsync(trace->hi, dtr.hi, sizeof(double) * per_axis, cudaMemcpyDeviceToHost, h->stream));
+        if (trace->counts_t) CT_CUDA(h, cudaMemcpyAsync(trace->counts_t, dtr.counts_t, sizeof(int64_t) * per_axis * bins, cudaMemcpyDeviceToHost, h->stream));
+        if (trace->counts_r) CT_CUDA(h, cudaMemcpyAsync(trace->counts_r, dtr.counts_r, sizeof(int64_t) * per_axis * bins, cudaMemcpyDeviceToHost, h->stream));
+        if (trace->lut) CT_CUDA(h, cudaMemcpyAsync(trace->lut, dtr.lut, sizeof(double) * per_axis * bins, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return first_bad_status(h, h->status, B);
+}
+
+}  // extern "C"

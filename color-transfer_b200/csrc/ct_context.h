@@ -1,0 +1,114 @@
+// Host-side context behind ct_handle and the internal launcher prototypes.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "ct_common.cuh"
+
+struct ct_context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    char err[512] = {0};
+    int64_t launches = 0;
+
+    // moments scratch: per-block partial sums + one ticket per pair
+    double *partials = nullptr;
+    size_t partials_doubles = 0;
+    unsigned int *tickets = nullptr;
+    // per-pair transform / status / raw sums when the caller passes NULL
+    double *xform = nullptr;
+    double *sums = nullptr;
+    int *status = nullptr;
+    int scratch_pairs = 0;
+    int *host_status = nullptr;  // pinned
+
+    // grow-only device workspace (IDT state, staging of host images)
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+
+    bool remap_smem_raised = false;
+
+    // host pipeline
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+};
+
+namespace ct {
+
+inline int fail(ct_context *h, int code, const char *fmt, ...) {
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CT_CUDA(h, expr)                                                                    \
+    do {                                                                                    \
+        cudaError_t e__ = (expr);                                                           \
+        if (e__ != cudaSuccess)                                                             \
+            return ct::fail((h), CT_E_CUDA, "%s failed: %s (%s:%d)", #expr,                 \
+                            cudaGetErrorString(e__), __FILE__, __LINE__);                   \
+    } while (0)
+
+#define CT_TRY(expr)                  \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != CT_OK) return rc__; \
+    } while (0)
+
+inline int src_kind(const ct_batch *b) { return b->dtype * 2 + b->layout; }
+inline size_t elem_size(int dtype) { return dtype == CT_F32 ? 4 : 8; }
+
+inline int64_t plane_of(const ct_batch *b) { return b->plane_stride ? b->plane_stride : b->npix; }
+
+// 128-bit accesses need: 16 B aligned base, image stride and (planar) plane stride multiples of
+// one vector.  HWC groups are 3 vectors, so any 16 B aligned image start works.
+inline bool vec_ok(const ct_batch *b) {
+    const size_t es = elem_size(b->dtype);
+    const int64_t per_vec = 16 / (int64_t)es;
+    if (((uintptr_t)b->data) & 15) return false;
+    if (b->count > 1 && (b->image_stride % per_vec)) return false;
+    if (b->layout == CT_CHW && (plane_of(b) % per_vec)) return false;
+    return true;
+}
+
+inline Img img_of(const ct_batch *b) {
+    return Img{b->data, b->npix, b->count > 1 ? b->image_stride : 0, plane_of(b)};
+}
+inline ImgOut imgout_of(const ct_batch *b) {
+    return ImgOut{b->data, b->npix, b->count > 1 ? b->image_stride : 0, plane_of(b)};
+}
+
+int check_batch(ct_context *h, const ct_batch *b, const char *name);
+int ensure_scratch(ct_context *h, int pairs);
+int ensure_partials(ct_context *h, size_t doubles);
+int ensure_ws(ct_context *h, size_t bytes);
+int ensure_stage(ct_context *h, size_t bytes);
+
+// ct_linear.cu
+int launch_moments(ct_context *h, const ct_batch *a, const ct_batch *b, int lab, double *sums,
+                   int method, double *xform, int *status);
+int launch_solve(ct_context *h, int method, const double *sums_t, const double *sums_r,
+                 int64_t sums_stride, int count, double *xform, int *status);
+int launch_apply(ct_context *h, int method, const ct_batch *target, const double *xform,
+                 const ct_batch *out);
+
+// ct_idt.cu
+int launch_keys_init(ct_context *h, int64_t *keys, int64_t n);
+int launch_ranges(ct_context *h, const ct_batch *img, const double *rot, int64_t rot_stride,
+                  int64_t *keys, int64_t keys_stride, int32_t *status);
+int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt_trace *trace,
+                int trace_iter, int trace_niter);
+int launch_lut(ct_context *h, const ct_idt_stage *s, int keep_counts, const ct_idt_trace *trace,
+               int trace_iter, int trace_niter);
+int launch_remap(ct_context *h, const ct_idt_stage *s, const ct_batch *dst, int round_f32);
+
+}  // namespace ct

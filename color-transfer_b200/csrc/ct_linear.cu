@@ -1,0 +1,316 @@
+// Linear (closed-form) transfers: K1 moments (+K1L Lab-fused), K2 one-warp 3x3 solve,
+// K3 affine remap (+K3L Lab-fused).  ref: methods/linear.py:8-124.
+#include "ct_context.h"
+#include "ct_lab.cuh"
+#include "ct_solve3.cuh"
+
+namespace ct {
+
+// ---------------------------------------------------------------------------------------------
+// K1 / K1L: single-pass raw moments about a fixed shift, fp64 accumulators, warp-shuffle tree,
+// one partial per block, last block of each pair combines all partials in block-index order
+// (deterministic: no floating-point atomics) and, when asked, runs the 3x3 solve in its first
+// warp.  Replaces np.mean/np.std/np.cov (linear.py:33-36, 64-67, 103-106).
+// ---------------------------------------------------------------------------------------------
+struct MomentsArgs {
+    Img img[2];
+    int kind[2];       // dtype*2 + layout
+    int vec[2];
+    int nimg;          // images per pair in this launch (1 or 2)
+    int lab;
+    double *partials;  // [B][nimg][gridDim.x][9]
+    unsigned int *tickets;
+    double *sums;      // [B][nimg][10]
+    int method;        // >= 0: fused solve (needs nimg == 2)
+    double *xform;     // [B][16]
+    int *status;       // [B]
+};
+
+template <bool LAB>
+__device__ __forceinline__ void accumulate(const double (&rgb)[3], double (&acc)[9]) {
+    double v[3];
+    if (LAB) {
+        lab::rgb2lab(rgb, v);
+        v[0] -= 50.0;
+    } else {
+        v[0] = rgb[0] - 0.5;
+        v[1] = rgb[1] - 0.5;
+        v[2] = rgb[2] - 0.5;
+    }
+    acc[0] += v[0];
+    acc[1] += v[1];
+    acc[2] += v[2];
+    acc[3] = fma(v[0], v[0], acc[3]);
+    acc[6] = fma(v[1], v[1], acc[6]);
+    acc[8] = fma(v[2], v[2], acc[8]);
+    if (!LAB) {  // Reinhard needs only the per-channel variances
+        acc[4] = fma(v[0], v[1], acc[4]);
+        acc[5] = fma(v[0], v[2], acc[5]);
+        acc[7] = fma(v[1], v[2], acc[7]);
+    }
+}
+
+template <typename IO, bool VEC, bool LAB>
+__device__ __forceinline__ void moments_image(const Img &im, int64_t pair, double (&acc)[9]) {
+    using T = typename IO::elem_t;
+    const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
+    constexpr int G = IO::G;
+    const int64_t ngroups = im.npix / G;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += stride) {
+        double x[G][3];
+        IO::template load<VEC>(base, im.plane_stride, g, x);
+#pragma unroll
+        for (int i = 0; i < G; ++i) accumulate<LAB>(x[i], acc);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t p = ngroups * G; p < im.npix; ++p) {
+            double x[3];
+            IO::load1(base, im.plane_stride, p, x);
+            accumulate<LAB>(x, acc);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) moments_kernel(MomentsArgs a) {
+    const int z = blockIdx.z;
+    const int64_t pair = blockIdx.y;
+    double acc[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+
+    const Img im = a.img[z];
+    const int sel = a.kind[z] * 2 + a.vec[z];
+    if (a.lab) {
+        switch (sel) {
+#define CT_CASE(ID, T, L, V) case ID: moments_image<PixelIO<T, L>, V, true>(im, pair, acc); break;
+            CT_FOR_EACH_SRC(CT_CASE)
+#undef CT_CASE
+        }
+    } else {
+        switch (sel) {
+#define CT_CASE(ID, T, L, V) case ID: moments_image<PixelIO<T, L>, V, false>(im, pair, acc); break;
+            CT_FOR_EACH_SRC(CT_CASE)
+#undef CT_CASE
+        }
+    }
+
+    __shared__ double red[kWarps][9];
+    __shared__ double total[2][10];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const double s = warp_sum(acc[i]);
+        if (lane == 0) red[warp][i] = s;
+    }
+    __syncthreads();
+    const int64_t nblk = gridDim.x;
+    double *mine = a.partials + (((int64_t)pair * a.nimg + z) * nblk + blockIdx.x) * 9;
+    if (threadIdx.x < 9) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
+        mine[threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&a.tickets[pair], 1u);
+        is_last = (t == (unsigned int)(nblk * a.nimg) - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    // fixed-order combine: thread (img, k) walks the partials of its image in block order
+    if (threadIdx.x < 9 * a.nimg) {
+        const int img = threadIdx.x / 9, k = threadIdx.x % 9;
+        const double *p = a.partials + ((int64_t)pair * a.nimg + img) * nblk * 9 + k;
+        double s = 0.0;
+        for (int64_t b = 0; b < nblk; ++b) s += __ldcg(p + b * 9);
+        total[img][1 + k] = s;
+        if (k == 0) total[img][0] = (double)a.img[img].npix;
+    }
+    __syncthreads();
+    if (threadIdx.x < 10 * a.nimg) {
+        const int img = threadIdx.x / 10, k = threadIdx.x % 10;
+        a.sums[((int64_t)pair * a.nimg + img) * 10 + k] = total[img][k];
+    }
+    if (threadIdx.x == 0) {
+        a.tickets[pair] = 0;  // ready for the next launch on this stream
+        if (a.method >= 0) {
+            const int st = solve3::solve(a.method, total[0], total[1], a.xform + pair * CT_XFORM_DOUBLES);
+            if (a.status) a.status[pair] = st;
+        }
+    }
+}
+
+// K2 standalone: one warp, lane = pair (used after an all-reduce of the sums, and by tests).
+__global__ void solve_kernel(int method, const double *sums_t, const double *sums_r,
+                             int64_t sums_stride, int count, double *xform, int *status) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= count) return;
+    const int st = solve3::solve(method, sums_t + pair * sums_stride, sums_r + pair * sums_stride,
+                                 xform + (int64_t)pair * CT_XFORM_DOUBLES);
+    if (status) status[pair] = st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 / K3L: out = (x - mu_t) @ M + mu_r per pixel; Reinhard wraps it in rgb2lab / lab2rgb+clip.
+// Pure streaming: 128-bit loads and stores, grid-stride, 2 x S bytes per pixel.
+// ---------------------------------------------------------------------------------------------
+struct ApplyArgs {
+    Img src;
+    ImgOut dst;
+    const double *xform;  // [B][16]
+};
+
+template <bool LAB>
+__device__ __forceinline__ void apply_pixel(const double *xf, const double (&x)[3], double (&y)[3]) {
+    if (LAB) {
+        double l[3], m[3];
+        lab::rgb2lab(x, l);
+        // (lab - mean_t) * std_r / std_t + mean_r   (linear.py:38)
+        m[0] = fma(l[0] - xf[9], xf[0], xf[12]);
+        m[1] = fma(l[1] - xf[10], xf[4], xf[13]);
+        m[2] = fma(l[2] - xf[11], xf[8], xf[14]);
+        lab::lab2rgb(m, y);
+    } else {
+        const double d0 = x[0] - xf[9], d1 = x[1] - xf[10], d2 = x[2] - xf[11];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) y[c] = fma(d2, xf[6 + c], fma(d1, xf[3 + c], d0 * xf[c])) + xf[12 + c];
+    }
+}
+
+template <typename SIO, typename DIO, bool VEC, bool LAB>
+__global__ void __launch_bounds__(kThreads) apply_kernel(ApplyArgs a) {
+    using TS = typename SIO::elem_t;
+    using TD = typename DIO::elem_t;
+    const int64_t pair = blockIdx.y;
+    __shared__ double xf[CT_XFORM_DOUBLES];
+    if (threadIdx.x < CT_XFORM_DOUBLES) xf[threadIdx.x] = a.xform[pair * CT_XFORM_DOUBLES + threadIdx.x];
+    __syncthreads();
+    const TS *src = reinterpret_cast<const TS *>(a.src.data) + pair * a.src.image_stride;
+    TD *dst = reinterpret_cast<TD *>(a.dst.data) + pair * a.dst.image_stride;
+    constexpr int G = SIO::G;
+    const int64_t ngroups = a.src.npix / G;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += stride) {
+        double x[G][3], y[G][3];
+        SIO::template load<VEC>(src, a.src.plane_stride, g, x);
+#pragma unroll
+        for (int i = 0; i < G; ++i) apply_pixel<LAB>(xf, x[i], y[i]);
+        DIO::template store<VEC, G>(dst, a.dst.plane_stride, g * G, y);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int64_t p = ngroups * G; p < a.src.npix; ++p) {
+            double x[3], y[3];
+            SIO::load1(src, a.src.plane_stride, p, x);
+            apply_pixel<LAB>(xf, x, y);
+            DIO::store1(dst, a.dst.plane_stride, p, y);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static int blocks_for(const ct_context *h, int64_t npix, int group, int64_t units, int per_sm) {
+    const int64_t want = (npix / group + kThreads - 1) / kThreads;
+    int64_t cap = ((int64_t)h->sm_count * per_sm) / (units > 0 ? units : 1);
+    if (cap < 1) cap = 1;
+    int64_t n = want < cap ? want : cap;
+    return (int)(n < 1 ? 1 : n);
+}
+
+int launch_moments(ct_context *h, const ct_batch *a, const ct_batch *b, int lab, double *sums,
+                   int method, double *xform, int *status) {
+    CT_TRY(check_batch(h, a, "images"));
+    const int nimg = b ? 2 : 1;
+    if (b) {
+        CT_TRY(check_batch(h, b, "reference"));
+        if (b->count != a->count) return fail(h, CT_E_INVALID, "target/reference batch counts differ");
+    }
+    if (!sums) return fail(h, CT_E_INVALID, "sums is NULL");
+    const int B = a->count;
+    int64_t npix_max = a->npix;
+    if (b && b->npix > npix_max) npix_max = b->npix;
+    const int nblk = blocks_for(h, npix_max, 2, (int64_t)B * nimg, 8);
+    CT_TRY(ensure_partials(h, (size_t)B * nimg * nblk * 9));
+    CT_TRY(ensure_scratch(h, B));
+    MomentsArgs m{};
+    m.img[0] = img_of(a);
+    m.kind[0] = src_kind(a);
+    m.vec[0] = vec_ok(a);
+    if (b) {
+        m.img[1] = img_of(b);
+        m.kind[1] = src_kind(b);
+        m.vec[1] = vec_ok(b);
+    }
+    m.nimg = nimg;
+    m.lab = lab;
+    m.partials = h->partials;
+    m.tickets = h->tickets;
+    m.sums = sums;
+    m.method = (b && xform) ? method : -1;
+    m.xform = xform;
+    m.status = status;
+    moments_kernel<<<dim3(nblk, B, nimg), kThreads, 0, h->stream>>>(m);
+    h->launches++;
+    CT_CUDA(h, cudaGetLastError());
+    return CT_OK;
+}
+
+int launch_solve(ct_context *h, int method, const double *sums_t, const double *sums_r,
+                 int64_t sums_stride, int count, double *xform, int *status) {
+    if (!sums_t || !sums_r || !xform || count <= 0) return fail(h, CT_E_INVALID, "bad solve arguments");
+    if (method < CT_REINHARD || method > CT_MKL_CHOLESKY) return fail(h, CT_E_INVALID, "unknown method %d", method);
+    solve_kernel<<<(count + 31) / 32, 32, 0, h->stream>>>(method, sums_t, sums_r, sums_stride, count, xform, status);
+    h->launches++;
+    CT_CUDA(h, cudaGetLastError());
+    return CT_OK;
+}
+
+template <typename SIO, bool LAB>
+static void launch_apply_dst(const ct_batch *out, bool vec, dim3 grid, cudaStream_t st, const ApplyArgs &a) {
+    if (out->dtype == CT_F32) {
+        if (vec) apply_kernel<SIO, PixelIO<float, CT_HWC>, true, LAB><<<grid, kThreads, 0, st>>>(a);
+        else apply_kernel<SIO, PixelIO<float, CT_HWC>, false, LAB><<<grid, kThreads, 0, st>>>(a);
+    } else {
+        if (vec) apply_kernel<SIO, PixelIO<double, CT_HWC>, true, LAB><<<grid, kThreads, 0, st>>>(a);
+        else apply_kernel<SIO, PixelIO<double, CT_HWC>, false, LAB><<<grid, kThreads, 0, st>>>(a);
+    }
+}
+
+int launch_apply(ct_context *h, int method, const ct_batch *target, const double *xform,
+                 const ct_batch *out) {
+    CT_TRY(check_batch(h, target, "target"));
+    CT_TRY(check_batch(h, out, "out"));
+    if (!xform) return fail(h, CT_E_INVALID, "xform is NULL");
+    if (out->npix != target->npix || out->count != target->count)
+        return fail(h, CT_E_INVALID, "out must have the target's npix and count");
+    if (out->layout != CT_HWC) return fail(h, CT_E_UNSUPPORTED, "linear output must be CT_HWC");
+    const bool vec = vec_ok(target) && vec_ok(out);
+    const int group = target->dtype == CT_F32 ? 4 : 2;
+    const int nblk = blocks_for(h, target->npix, group, target->count, 16);
+    const dim3 grid(nblk, target->count);
+    ApplyArgs a{img_of(target), imgout_of(out), xform};
+    const bool labm = method == CT_REINHARD;
+    switch (src_kind(target)) {
+#define CT_APPLY(T, L)                                                                   \
+    if (labm) launch_apply_dst<PixelIO<T, L>, true>(out, vec, grid, h->stream, a);      \
+    else launch_apply_dst<PixelIO<T, L>, false>(out, vec, grid, h->stream, a);          \
+    break;
+        case 0: CT_APPLY(float, CT_HWC)
+        case 1: CT_APPLY(float, CT_CHW)
+        case 2: CT_APPLY(double, CT_HWC)
+        case 3: CT_APPLY(double, CT_CHW)
+#undef CT_APPLY
+    }
+    h->launches++;
+    CT_CUDA(h, cudaGetLastError());
+    return CT_OK;
+}
+
+}  // namespace ct

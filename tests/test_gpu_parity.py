@@ -1,0 +1,213 @@
+"""GPU parity tests: the CUDA path, called through the reference-facing Python functions (which
+go through the C ABI), against the CPU oracle on identical inputs.
+
+Gates (BASELINE.json north_star): histogram counts / ranges / tables bit-exact; float outputs
+within 1e-4 max-abs on [0,1]; uint8-rounded output identical for >= 99.99 % of values."""
+
+import numpy as np
+import pytest
+
+from conftest import synthetic_pair, u8_identical_fraction
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4          # north_star: float outputs within 1e-4 max-abs
+U8_MIN = 0.9999     # north_star: uint8 identical for >= 99.99 %
+
+
+@pytest.fixture(scope="module")
+def api():
+    import methods.iterative
+    import methods.linear
+    from oracle import reference_numpy as oracle
+    return methods.linear, methods.iterative, oracle
+
+
+def _close(out, ref, tol=TOL, u8=U8_MIN):
+    assert out.shape == ref.shape
+    err = float(np.max(np.abs(out.astype(np.float64) - ref.astype(np.float64))))
+    frac = u8_identical_fraction(out, ref)
+    assert err <= tol, f"max-abs {err:.3e} > {tol}"
+    assert frac >= u8, f"uint8-identical fraction {frac:.6f} < {u8}"
+    return err, frac
+
+
+PAIRS = [(24, 40, None), (37, 53, None), (64, 96, (48, 80)), (1, 7, None), (128, 128, None)]
+
+
+@pytest.mark.parametrize("h,w,ref_shape", PAIRS)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_mkl_and_ccs(api, h, w, ref_shape, dtype):
+    lin, _, oracle = api
+    t, r = synthetic_pair(h, w, 11, dtype, ref_shape)
+    t64, r64 = t.astype(np.float64), r.astype(np.float64)   # gate = float64 oracle
+    for dec in ("MK", "sqrt", "cholesky"):
+        out = lin.monge_kantorovitch_color_transfer(t, r, decomposition=dec)
+        assert out.dtype == np.float64
+        err, _ = _close(out, oracle.monge_kantorovitch_color_transfer(t64, r64, dec))
+        assert err < 1e-9
+    out = lin.color_transfer_in_correlated_color_space(t, r)
+    ref = oracle.color_transfer_in_correlated_color_space(t64, r64)
+    err = float(np.max(np.abs(out - ref)))
+    if err > TOL:  # LAPACK's free singular-vector signs: compare after aligning them
+        mu_t, cov_t = oracle.mean_and_cov(t64)
+        mu_r, cov_r = oracle.mean_and_cov(r64)
+        best = min(
+            float(np.max(np.abs(out - ((t64.reshape(-1, 3) - mu_t) @ oracle.ccs_matrix(cov_t, cov_r, s).T + mu_r).reshape(t.shape))))
+            for s in [(a, b, c) for a in (1, -1) for b in (1, -1) for c in (1, -1)])
+        assert best <= 1e-8, f"CCS differs from every sign choice: {best:.3e}"
+
+
+@pytest.mark.parametrize("h,w,ref_shape", PAIRS)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_reinhard(api, h, w, ref_shape, dtype):
+    lin, _, oracle = api
+    t, r = synthetic_pair(h, w, 12, dtype, ref_shape)
+    out = lin.color_transfer_between_images(t, r)
+    assert out.dtype == dtype
+    assert out.min() >= 0.0 and out.max() <= 1.0
+    ref = oracle.color_transfer_between_images(t.astype(np.float64), r.astype(np.float64))
+    _close(out, ref, u8=0.999 if h * w < 5000 else U8_MIN)
+
+
+def test_mkl_unknown_decomposition(api):
+    lin, _, _ = api
+    t, r = synthetic_pair(8, 8, 1)
+    with pytest.raises(ValueError, match="Unknown decomposition"):
+        lin.monge_kantorovitch_color_transfer(t, r, decomposition="qr")
+
+
+def test_cholesky_not_positive_definite(api):
+    lin, _, _ = api
+    t = np.full((8, 8, 3), 0.25)      # constant image: zero covariance
+    _, r = synthetic_pair(8, 8, 2)
+    with pytest.raises(np.linalg.LinAlgError):
+        lin.monge_kantorovitch_color_transfer(t, r, decomposition="cholesky")
+
+
+def test_inputs_not_modified_and_runner_layout(api):
+    """The reference Runner hands over float32 HWC *views* of CHW memory (methods/__init__.py:21-22)."""
+    lin, it, oracle = api
+    t, r = synthetic_pair(45, 67, 5, np.float32)
+    t_chw = np.ascontiguousarray(t.transpose(2, 0, 1))
+    r_chw = np.ascontiguousarray(r.transpose(2, 0, 1))
+    tv, rv = t_chw.transpose(1, 2, 0), r_chw.transpose(1, 2, 0)
+    assert not tv.flags.c_contiguous
+    keep_t, keep_r = t_chw.copy(), r_chw.copy()
+    out = lin.monge_kantorovitch_color_transfer(tv, rv)
+    _close(out, oracle.monge_kantorovitch_color_transfer(t.astype(np.float64), r.astype(np.float64)))
+    out = lin.color_transfer_between_images(tv, rv)
+    _close(out, oracle.color_transfer_between_images(t.astype(np.float64), r.astype(np.float64)), u8=0.999)
+    np.random.seed(3)
+    out = it.iterative_distribution_transfer(tv, rv)
+    np.random.seed(3)
+    _close(out, oracle.iterative_distribution_transfer(t, r))
+    assert np.array_equal(t_chw, keep_t) and np.array_equal(r_chw, keep_r)
+    # a strided slice is neither layout: the wrapper must still give the right answer
+    big_t, big_r = synthetic_pair(40, 60, 6)
+    out = lin.monge_kantorovitch_color_transfer(big_t[::2, ::3], big_r[::2, ::3])
+    _close(out, oracle.monge_kantorovitch_color_transfer(np.ascontiguousarray(big_t[::2, ::3]), np.ascontiguousarray(big_r[::2, ::3])))
+
+
+def _check_idt_trace(trace, traces_o, exact_from=0):
+    n_iter = len(traces_o)
+    for i in range(n_iter):
+        o = traces_o[i]
+        assert np.array_equal(trace["counts_t"][i], o["counts_t"]), f"target counts differ at iteration {i}"
+        assert np.array_equal(trace["counts_r"][i], o["counts_r"]), f"reference counts differ at iteration {i}"
+        if i <= exact_from:
+            assert np.array_equal(trace["lo"][i], o["lo"]) and np.array_equal(trace["hi"][i], o["hi"])
+            assert np.array_equal(trace["lut"][i], o["lut"]), f"inverse-CDF table differs at iteration {i}"
+        else:   # the state differs from LAPACK's solve by rounding only
+            np.testing.assert_allclose(trace["lo"][i], o["lo"], rtol=0, atol=1e-13)
+            np.testing.assert_allclose(trace["hi"][i], o["hi"], rtol=0, atol=1e-13)
+            np.testing.assert_allclose(trace["lut"][i], o["lut"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("h,w,ref_shape", PAIRS[:3] + [(96, 128, None)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_idt_bit_exact_stages(api, h, w, ref_shape, dtype):
+    _, it, oracle = api
+    t, r = synthetic_pair(h, w, 21, dtype, ref_shape)
+    np.random.seed(42)
+    ref, traces_o = oracle.idt_instrumented(t, r)          # the reference's own dtype flow
+    np.random.seed(42)
+    trace = {}
+    out = it.iterative_distribution_transfer(t, r, trace=trace)
+    assert out.dtype == np.float64 and out.shape == t.shape
+    assert np.array_equal(trace["rot"], np.stack([x["rot"] for x in traces_o]))
+    _check_idt_trace(trace, traces_o)
+    err, _ = _close(out, ref)
+    assert err < 1e-11
+
+
+@pytest.mark.parametrize("bins,n_iter", [(64, 2), (255, 1), (300, 3), (1024, 2), (2, 2), (1, 1)])
+def test_idt_other_arguments(api, bins, n_iter):
+    _, it, oracle = api
+    t, r = synthetic_pair(50, 70, 22)
+    np.random.seed(7)
+    ref, traces_o = oracle.idt_instrumented(t, r, bins=bins, n_iter=n_iter)
+    np.random.seed(7)
+    trace = {}
+    out = it.iterative_distribution_transfer(t, r, bins=bins, n_iter=n_iter, trace=trace)
+    _check_idt_trace(trace, traces_o)
+    _close(out, ref, tol=1e-10)
+
+
+def test_idt_rng_stream_and_zero_iterations(api):
+    _, it, oracle = api
+    t, r = synthetic_pair(16, 16, 23)
+    np.random.seed(5)
+    it.iterative_distribution_transfer(t, r, n_iter=3)
+    after_ours = np.random.random()
+    np.random.seed(5)
+    oracle.iterative_distribution_transfer(t, r, n_iter=3)
+    assert after_ours == np.random.random()      # the global RNG advanced identically
+    assert np.array_equal(it.iterative_distribution_transfer(t, r, n_iter=0), t)
+
+
+def test_idt_nonfinite_raises(api):
+    _, it, _ = api
+    t, r = synthetic_pair(16, 16, 24)
+    t = t.copy()
+    t[3, 4, 1] = np.nan
+    with pytest.raises(ValueError):
+        it.iterative_distribution_transfer(t, r)
+
+
+def test_idt_constant_target(api):
+    """lo == hi on no axis here, but a constant target exercises empty bins and CDF ties."""
+    _, it, oracle = api
+    _, r = synthetic_pair(20, 30, 25)
+    t = np.full((20, 30, 3), 0.5)
+    np.random.seed(9)
+    ref = oracle.iterative_distribution_transfer(t, r)
+    np.random.seed(9)
+    out = it.iterative_distribution_transfer(t, r)
+    _close(out, ref, tol=1e-10)
+
+
+def test_pair0964_all_methods(api, pair0964, golden):
+    """configs[0] and configs[1] of BASELINE.json: the reference's own stereo pair, float64."""
+    lin, it, oracle = api
+    left, right = pair0964
+    g = golden["pair0964"]
+    stride = 997
+    out = lin.monge_kantorovitch_color_transfer(left, right)
+    assert np.max(np.abs(out.reshape(-1)[::stride] - g["mkl_MK_sample"])) < 1e-10
+    _close(out, oracle.monge_kantorovitch_color_transfer(left, right))
+    out = lin.color_transfer_in_correlated_color_space(left, right)
+    assert np.max(np.abs(out.reshape(-1)[::stride] - g["ccs_sample"])) < 1e-9   # signs agree on this pair
+    out = lin.color_transfer_between_images(left, right)
+    assert np.max(np.abs(out.reshape(-1)[::stride] - g["reinhard_sample"])) < TOL
+    _close(out, oracle.color_transfer_between_images(left, right))
+    np.random.seed(42)
+    trace = {}
+    out = it.iterative_distribution_transfer(left, right, trace=trace)
+    assert np.array_equal(trace["counts_t"], g["idt_counts_t"])
+    assert np.array_equal(trace["counts_r"], g["idt_counts_r"])
+    assert np.array_equal(trace["lo"][0], g["idt_lo"][0]) and np.array_equal(trace["hi"][0], g["idt_hi"][0])
+    assert np.array_equal(trace["lut"][0], g["idt_lut"][0])
+    assert np.max(np.abs(out.reshape(-1)[::stride] - g["idt_sample"])) < 1e-10
+    np.random.seed(42)
+    _close(out, oracle.iterative_distribution_transfer(left, right))
