@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py - stereopair Mpix/s of the B200 colour-transfer path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[3] - synthetic 4K VR180 stereo video,
+3840x2160 per eye, float32 HWC frames (the reference CLI dtype), iterative distribution
+transfer with bins=255, n_iter=4, rotations pre-drawn per frame after np.random.seed(42),
+frames sharded frame-parallel over the ranks with no data-path collective (weak scaling:
+every rank processes --frames frames per step).  A "step" is one pass of IDT over one batch
+of frames.
+
+value      device-resident: frames already in HBM, CUDA-event time on the launching stream.
+e2e        the batched host API (color_transfer_b200.batch.idt_frames -> ct_idt_transfer_host):
+           pinned host frames in, pinned float64 result out, copies inside the timed region.
+roofline   the dominant kernel (largest share of the step), algorithmic bytes / its CUDA-event
+           time, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline  the numpy oracle port (the reference's own numpy calls) on host cores, bounded
+           sample, rank 0 at N=1 only.
+--impl reference  the same oracle port with a process pool over frames on all usable cores.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H4K, W4K = 2160, 3840
+BINS, N_ITER = 255, 4
+METRIC = "stereopair Mpix/s (IDT, 4K stereo video, frame-parallel)"
+# algorithmic bytes per target pixel, IDT, float32 frames, n_iter=4 (SURVEY.md 8d / BASELINE.md 4)
+IDT_BYTES_PER_PIXEL_F32 = 24 + (24 + 36) + 3 * (36 + 48)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=8, help="frame pairs per rank per step")
+    ap.add_argument("--e2e-frames", type=int, default=4)
+    ap.add_argument("--height", type=int, default=H4K)
+    ap.add_argument("--width", type=int, default=W4K)
+    ap.add_argument("--stress", action="store_true", help="i.i.d. uniform frames instead of the smooth field")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.tmp.name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_frame(args):
+    """One oracle IDT on one synthetic frame pair; runs in a worker process."""
+    seed, h, w, rotations, blas_threads = args
+    import numpy as np
+    if blas_threads:
+        try:
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(blas_threads)
+        except Exception:  # noqa: BLE001
+            pass
+    from color_transfer_b200_synth import frame_pair  # registered by _register_synth()
+    from oracle import reference_numpy as oracle
+    t, r = frame_pair(h, w, seed, np.float32)
+    t0 = time.perf_counter()
+    oracle.iterative_distribution_transfer(t, r, BINS, N_ITER, rotations=rotations)
+    return time.perf_counter() - t0
+
+
+def _register_synth():
+    """Load color-transfer_b200/synth.py without importing the package (no CUDA needed)."""
+    import importlib.util
+    if "color_transfer_b200_synth" in sys.modules:
+        return
+    spec = importlib.util.spec_from_file_location(
+        "color_transfer_b200_synth", os.path.join(ROOT, "color-transfer_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["color_transfer_b200_synth"] = mod
+    spec.loader.exec_module(mod)
+
+
+def usable_workers(bytes_per_worker):
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        import psutil
+        n = min(n, max(1, int(psutil.virtual_memory().available * 0.5 // bytes_per_worker)))
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, min(n, 64))
+
+
+def cpu_oracle_throughput(h, w, workers, waves, first_seed=2000):
+    """Mpix/s of the oracle port: `workers` frames in flight, `waves` rounds."""
+    import multiprocessing as mp
+
+    import numpy as np
+    import scipy.stats
+    _register_synth()
+    np.random.seed(42)
+    jobs = []
+    for k in range(workers * waves):
+        rot = np.stack([scipy.stats.special_ortho_group.rvs(3) for _ in range(N_ITER)])
+        jobs.append((first_seed + k, h, w, rot, 1 if workers > 1 else 0))
+    t0 = time.perf_counter()
+    if workers == 1:
+        busy = [_cpu_frame(j) for j in jobs]
+        wall = sum(busy)          # exclude the synthetic-frame generation
+    else:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(workers) as pool:
+            busy = pool.map(_cpu_frame, jobs, chunksize=1)
+        # frames run concurrently: the wall time of the transfer part is the slowest lane
+        lanes = [sum(busy[i::workers]) for i in range(workers)]
+        wall = max(lanes)
+    total_wall = time.perf_counter() - t0
+    mpix = len(jobs) * h * w / 1e6
+    return mpix / wall, wall, total_wall
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: quarter-area crops of the 4K frames (IDT cost is linear in pixels)
+    h, w = a.height // 2, a.width // 2
+    workers = usable_workers(bytes_per_worker=h * w * 3 * 8 * 14)
+    values = []
+    for _ in range(a.warmup if a.warmup < 2 else 1):
+        cpu_oracle_throughput(h, w, workers, 1)
+    t_steps = []
+    for s in range(a.steps):
+        v, wall, _ = cpu_oracle_throughput(h, w, workers, 1, first_seed=2000 + s * workers)
+        values.append(v)
+        t_steps.append(wall)
+    value = sum(values) / len(values)
+    sample = (f"{workers} frames in flight per step (one per process), each a {w}x{h} quarter-area frame of the "
+              f"4K workload, float32 in, bins={BINS}, n_iter={N_ITER}; numpy oracle port of methods/iterative.py")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * sum(t_steps) / len(t_steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, frames=workers),
+        "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(a, frames):
+    return {"workload": "configs[3]: synthetic 4K VR180 stereo video, IDT frame-parallel",
+            "frame": [a.height, a.width, 3], "frames_per_rank_per_step": frames, "input_dtype": "float32",
+            "bins": BINS, "n_iter": N_ITER, "distribution": "uniform-noise" if a.stress else "smooth-field+noise",
+            "parallelism": f"frame-parallel x{a.gpus}, no collective",
+            "l2": "working set per frame (99.5 MB/eye in, 199 MB state) exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import color_transfer_b200  # noqa: F401
+    from color_transfer_b200 import _cabi, batch, device, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    handle = _cabi.default_handle(local)
+    H, W, F = a.height, a.width, a.frames
+    npix = H * W
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # frames k = rank, rank + world, ...: rotations pre-drawn in frame order after seed 42
+    np.random.seed(42)
+    all_rot = np.stack([batch.draw_rotations(N_ITER) for _ in range(F * world)])
+    my_rot = torch.from_numpy(all_rot[rank::world].copy()).to(dev)
+    tgt, ref = synth.frame_pairs_cuda(F, H, W, 2000 + rank, dev, stress=a.stress)
+    out = torch.empty((F, H, W, 3), dtype=torch.float64, device=dev)
+    ws = device.idt_workspace(npix, F, BINS, N_ITER, dev)
+
+    def step():
+        device.idt_transfer(tgt, ref, my_rot, BINS, N_ITER, out=out, workspace=ws, handle=handle)
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = handle.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = handle.launches - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / a.steps
+    value = world * F * npix / 1e6 / (ms_step / 1e3)
+
+    # ---- per-kernel breakdown with CUDA events (stage API == the same kernels, unfused LUT off)
+    stages = device.IdtStages(tgt, ref, my_rot, BINS, N_ITER, handle=handle)
+    times = {}
+
+    class Timer:
+        def __init__(self, name):
+            self.name = name
+
+        def __enter__(self):
+            self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+        def __exit__(self, *exc):
+            self.b.record()
+            self.b.synchronize()
+            times.setdefault(self.name, []).append(self.a.elapsed_time(self.b))
+
+    stages.run(timer=Timer)
+    times.clear()
+    for _ in range(3):
+        stages.run(timer=Timer)
+    del stages
+    kern = {}
+    for name, v in times.items():
+        kind = name.split("_")[0]
+        kern.setdefault(kind, []).append((name, sum(v) / len(v)))
+    share = {k: sum(t for _, t in v) for k, v in kern.items()}
+    dominant = max(share, key=share.get)
+    # algorithmic bytes per pixel of each launch of the dominant kernel (float32 frames, fp64 state)
+    per_launch_bytes = {"hist": lambda it: (12 if it == 0 else 24) + 12, "remap": lambda it: (12 if it == 0 else 24) + 24,
+                        "ranges": lambda it: 12}
+    achieved = []
+    for name, ms in kern[dominant]:
+        it = int(name.split("_")[1]) if name.split("_")[1].isdigit() else 0
+        achieved.append(per_launch_bytes[dominant](it) * npix * F / (ms / 1e3) / 1e9)
+    peak, peak_kind = measured_peaks()
+    ach = sum(achieved) / len(achieved)
+    roofline = {"bound": "hbm", "kernel": {"hist": "hist_kernel", "remap": "remap_kernel", "ranges": "ranges_kernel"}[dominant],
+                "achieved": ach, "peak": peak, "peak_source": peak_kind, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None,
+                "kernel_ms": {k: round(sum(t for _, t in v), 4) for k, v in kern.items()},
+                "step_algorithmic_GBps": IDT_BYTES_PER_PIXEL_F32 * npix * F / (ms_step / 1e3) / 1e9,
+                "step_frac": IDT_BYTES_PER_PIXEL_F32 * npix * F / (ms_step / 1e3) / 1e9 / peak}
+
+    # ---- end to end through the batched host API, pinned buffers, copies inside the timed region
+    Fe = min(a.e2e_frames, F)
+    ht = batch.pinned_empty((Fe, H, W, 3), np.float32)
+    hr = batch.pinned_empty((Fe, H, W, 3), np.float32)
+    ho = batch.pinned_empty((Fe, H, W, 3), np.float64)
+    ht[...] = tgt[:Fe].cpu().numpy()
+    hr[...] = ref[:Fe].cpu().numpy()
+    rot_e2e = all_rot[rank::world][:Fe]
+    handle.set_stream(0)
+    batch.idt_frames(ht, hr, BINS, N_ITER, rotations=rot_e2e, out=ho, handle=handle)
+    e2e_steps = max(2, min(a.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        batch.idt_frames(ht, hr, BINS, N_ITER, rotations=rot_e2e, out=ho, handle=handle)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    e2e = {"value": world * Fe * npix / 1e6 / e2e_s, "unit": "Mpix/s", "h2d_bytes_per_step": int(2 * Fe * npix * 12),
+           "d2h_bytes_per_step": int(Fe * npix * 24), "frames_per_step": Fe, "ms_per_step": e2e_s * 1e3,
+           "api": "color_transfer_b200.batch.idt_frames -> ct_idt_transfer_host"}
+    # the device-resident result and the host-API result must agree (same kernels)
+    same = bool(np.array_equal(ho[0], out[0].cpu().numpy()))
+
+    extras = {}
+    if not a.no_extras and rank == 0:
+        extras = linear_extras(torch, device, synth, _cabi, handle, dev, peak)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        hh, ww = H // 2, W // 2
+        v, wall, _ = cpu_oracle_throughput(hh, ww, 1, 1)
+        cpu = {"value": v, "unit": "Mpix/s", "cores": 1, "kind": "port",
+               "sample": f"one {ww}x{hh} quarter-area frame pair of the workload, float32 in, bins={BINS}, n_iter={N_ITER}, "
+                         f"single process ({wall:.1f} s); numpy oracle port of methods/iterative.py"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, F),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu, "host_api_matches_device_api": same, "extras": extras}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def linear_extras(torch, device, synth, _cabi, handle, dev, peak):
+    """Secondary numbers for the linear transfers (configs[2] shape: 960x540 float32 pairs)."""
+    out = {}
+    B, H, W = 64, 540, 960
+    tgt, ref = synth.frame_pairs_cuda(B, H, W, 1000, dev)
+    for name, method, bpp in (("reinhard_f32", _cabi.CT_REINHARD, 48), ("mkl_f32_to_f64", _cabi.CT_MKL_MK, 60)):
+        dst = torch.empty((B, H, W, 3), dtype=torch.float32 if method == _cabi.CT_REINHARD else torch.float64, device=dev)
+        for _ in range(3):
+            device.linear_transfer(method, tgt, ref, out=dst, handle=handle)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        reps = 10
+        for _ in range(reps):
+            device.linear_transfer(method, tgt, ref, out=dst, handle=handle)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbps = bpp * B * H * W / (ms / 1e3) / 1e9
+        out[name] = {"Mpix/s": B * H * W / 1e6 / (ms / 1e3), "ms_per_batch": ms, "pairs": B, "shape": [H, W, 3],
+                     "algorithmic_GBps": gbps, "frac_of_hbm": gbps / peak,
+                     "note": "batch working set 1.2-2.0 GB, larger than L2"}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,191 @@
+"""Device-resident API: the same transfers on torch CUDA tensors, no host round trip.
+
+PyTorch is only the allocator / stream provider here: tensors are handed to libct_b200.so as raw
+device pointers, kernels are ordered on torch's current stream, so ``torch.cuda.Event`` times
+them.  ``IdtStages`` exposes the per-stage C-ABI calls (ranges / hist / lut / remap) so that
+callers can time each kernel or insert a collective between stages (row-sharded mode).
+"""
+
+import ctypes
+
+import torch
+
+from . import _cabi
+
+_TORCH_DTYPE = {torch.float32: _cabi.CT_F32, torch.float64: _cabi.CT_F64}
+
+
+def _check_images(x, name):
+    if not x.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if x.dtype not in _TORCH_DTYPE:
+        raise ValueError(f"{name} must be float32 or float64")
+    if x.dim() == 3:
+        x = x.unsqueeze(0)
+    if x.dim() != 4 or x.shape[-1] != 3:
+        raise ValueError(f"{name} must be [H,W,3] or [B,H,W,3]")
+    return x
+
+
+def batch_of(x):
+    """ct_batch for a [B,H,W,3] tensor that is either contiguous (HWC) or a permuted view of
+    contiguous [B,3,H,W] memory (CHW)."""
+    b, h, w, _ = x.shape
+    npix = h * w
+    if x.is_contiguous():
+        layout, keep = _cabi.CT_HWC, x
+    elif x.permute(0, 3, 1, 2).is_contiguous():
+        layout, keep = _cabi.CT_CHW, x
+    else:
+        keep = x.contiguous()
+        layout = _cabi.CT_HWC
+    return _cabi.Batch(ctypes.c_void_p(keep.data_ptr()), npix, 3 * npix, 0, b, _TORCH_DTYPE[x.dtype], layout, 0), keep
+
+
+def _handle_for(x, handle):
+    h = handle or _cabi.default_handle(x.device.index or 0)
+    h.set_stream(torch.cuda.current_stream(x.device).cuda_stream)
+    return h
+
+
+def linear_transfer(method, target, reference, out=None, handle=None):
+    """method: _cabi.CT_REINHARD | CT_CCS | CT_MKL_*.  Returns a tensor shaped like target
+    (float64, or the target's dtype for Reinhard).  Asynchronous on the current stream."""
+    t = _check_images(target, "target")
+    r = _check_images(reference, "reference")
+    h = _handle_for(t, handle)
+    out_dtype = t.dtype if method == _cabi.CT_REINHARD else torch.float64
+    if out is None:
+        out = torch.empty(t.shape, dtype=out_dtype, device=t.device)
+    o = _check_images(out, "out")
+    tb, k1 = batch_of(t)
+    rb, k2 = batch_of(r)
+    ob, k3 = batch_of(o)
+    if k3 is not o:
+        raise ValueError("out must be contiguous")
+    h.check(h.lib.ct_linear_transfer(h.h, method, tb, rb, ob, None, None))
+    return out.view(target.shape) if target.dim() == 3 else out
+
+
+def idt_transfer(target, reference, rotations, bins=255, n_iter=4, out=None, workspace=None, handle=None):
+    """Fused IDT driver (2 + 2*n_iter launches).  rotations: float64 CUDA tensor
+    [B, n_iter, 3, 3].  Asynchronous on the current stream."""
+    t = _check_images(target, "target")
+    r = _check_images(reference, "reference")
+    h = _handle_for(t, handle)
+    b = t.shape[0]
+    rot = rotations.reshape(b, n_iter, 9)
+    if rot.dtype != torch.float64 or not rot.is_cuda or not rot.is_contiguous():
+        raise ValueError("rotations must be a contiguous float64 CUDA tensor [B, n_iter, 3, 3]")
+    if out is None:
+        out = torch.empty(t.shape, dtype=torch.float64, device=t.device)
+    o = _check_images(out, "out")
+    tb, k1 = batch_of(t)
+    rb, k2 = batch_of(r)
+    ob, k3 = batch_of(o)
+    if k3 is not o or o.dtype != torch.float64:
+        raise ValueError("out must be a contiguous float64 tensor")
+    ws_ptr, ws_bytes = (None, 0)
+    if workspace is not None:
+        ws_ptr, ws_bytes = ctypes.c_void_p(workspace.data_ptr()), workspace.numel() * workspace.element_size()
+    h.check(h.lib.ct_idt_transfer(h.h, tb, rb, ob, ctypes.c_void_p(rot.data_ptr()), bins, n_iter,
+                                  ws_ptr, ws_bytes, None, None))
+    return out.view(target.shape) if target.dim() == 3 else out
+
+
+def idt_workspace(npix, count, bins, n_iter, device):
+    n = _cabi.load_library().ct_idt_workspace_bytes(npix, count, bins, n_iter)
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+class IdtStages:
+    """IDT with every stage a separate call on caller-visible buffers.
+
+    ``between(name, tensor)`` is invoked after the stages that produce a globally reduced
+    quantity: ("keys", int64 [B, 6], to be MIN-reduced) once both images have folded their
+    projected range of an iteration, and ("counts", int64 [B, 2, 3, bins], to be SUM-reduced)
+    after the histograms - the row-sharded driver all-reduces them there.
+    ``timer(name)`` may return a context manager to time individual launches.
+    """
+
+    def __init__(self, target, reference, rotations, bins=255, n_iter=4, handle=None):
+        self.t = _check_images(target, "target")
+        self.r = _check_images(reference, "reference")
+        self.h = _handle_for(self.t, handle)
+        self.bins, self.n_iter = bins, n_iter
+        b, hh, ww, _ = self.t.shape
+        dev = self.t.device
+        self.B, self.npix = b, hh * ww
+        self.rot = rotations.reshape(b, n_iter, 9).contiguous()
+        self.keys = torch.empty((b, n_iter + 1, _cabi.CT_IDT_KEYS), dtype=torch.int64, device=dev)
+        self.counts = torch.zeros((b, 2, 3, bins), dtype=torch.int64, device=dev)
+        self.lut = torch.empty((b, _cabi.lut_doubles(bins)), dtype=torch.float64, device=dev)
+        self.status = torch.zeros((b,), dtype=torch.int32, device=dev)
+        self.plane = (self.npix + 1) // 2 * 2
+        self.state = torch.empty((b, 3, self.plane), dtype=torch.float64, device=dev) if n_iter >= 2 else None
+        self.out = torch.empty(self.t.shape, dtype=torch.float64, device=dev)
+        self.tb, self._k1 = batch_of(self.t)
+        self.rb, self._k2 = batch_of(self.r)
+        self.ob, _ = batch_of(self.out)
+        if self.state is not None:
+            self.sb = _cabi.Batch(ctypes.c_void_p(self.state.data_ptr()), self.npix, 3 * self.plane, self.plane, b,
+                                  _cabi.CT_F64, _cabi.CT_CHW, 0)
+
+    def _stage(self, it):
+        last = it == self.n_iter - 1
+        s = _cabi.IdtStage()
+        s.target = ctypes.pointer(self.tb if it == 0 else self.sb)
+        s.reference = ctypes.pointer(self.rb)
+        s.rot = self.rot.data_ptr() + it * 72
+        s.rot_next = None if last else self.rot.data_ptr() + (it + 1) * 72
+        s.rot_stride = self.n_iter * 9
+        s.keys = self.keys.data_ptr() + it * 48
+        s.keys_next = None if last else self.keys.data_ptr() + (it + 1) * 48
+        s.keys_stride = (self.n_iter + 1) * _cabi.CT_IDT_KEYS
+        s.counts = self.counts.data_ptr()
+        s.lut = self.lut.data_ptr()
+        s.status = self.status.data_ptr()
+        s.bins = self.bins
+        return s
+
+    def run(self, between=None, timer=None, fuse_lut=None):
+        import contextlib
+        h, lib = self.h, self.h.lib
+        if fuse_lut is None:
+            fuse_lut = between is None
+        tm = timer or (lambda name: contextlib.nullcontext())
+        self.counts.zero_()
+        self.status.zero_()
+        h.check(lib.ct_idt_keys_init(h.h, ctypes.c_void_p(self.keys.data_ptr()), self.keys.numel()))
+        ks, rs = (self.n_iter + 1) * _cabi.CT_IDT_KEYS, self.n_iter * 9
+        with tm("ranges_target"):
+            h.check(lib.ct_idt_ranges(h.h, self.tb, ctypes.c_void_p(self.rot.data_ptr()), rs,
+                                      ctypes.c_void_p(self.keys.data_ptr()), ks, ctypes.c_void_p(self.status.data_ptr())))
+        with tm("ranges_reference"):
+            h.check(lib.ct_idt_ranges(h.h, self.rb, ctypes.c_void_p(self.rot.data_ptr()), rs,
+                                      ctypes.c_void_p(self.keys.data_ptr()), ks, ctypes.c_void_p(self.status.data_ptr())))
+        if between:
+            between("keys", self.keys[:, 0])
+        for it in range(self.n_iter):
+            last = it == self.n_iter - 1
+            s = self._stage(it)
+            with tm(f"hist_{it}"):
+                h.check(lib.ct_idt_hist(h.h, ctypes.byref(s), 1 if fuse_lut else 0))
+            if not fuse_lut:
+                if between:
+                    between("counts", self.counts)
+                with tm(f"lut_{it}"):
+                    h.check(lib.ct_idt_lut(h.h, ctypes.byref(s), 0))
+            with tm(f"remap_{it}"):
+                h.check(lib.ct_idt_remap(h.h, ctypes.byref(s), self.ob if last else self.sb,
+                                         1 if (it == 0 and self.t.dtype == torch.float32) else 0))
+            if between and not last:
+                between("keys", self.keys[:, it + 1])
+        return self.out
+
+    def raise_for_status(self):
+        st = self.status.cpu()
+        if (st == _cabi.CT_E_NONFINITE).any():
+            raise ValueError("supplied range of projected values is not finite")
+        if (st != 0).any():
+            raise _cabi.CtError(int(st[st != 0][0]), "IDT kernel reported an error")

@@ -169,8 +169,9 @@ def back_rotate(rot, moved, projected, state):
     return np.linalg.solve(rot, moved - projected).T + state
 
 
-def idt_iteration(state, reference, rot, bins, moved_dtype):
-    """One full iteration; returns the new state and a dict of every intermediate."""
+def idt_iteration(state, reference, rot, bins, moved_dtype, keep_arrays=True):
+    """One full iteration; returns the new state and a dict of every intermediate
+    (the per-pixel arrays only when ``keep_arrays``)."""
     p_t = project(rot, state)
     p_r = project(rot, reference)
     moved = np.empty(p_t.shape, dtype=moved_dtype)      # np.empty_like(target.T), :36
@@ -187,12 +188,15 @@ def idt_iteration(state, reference, rot, bins, moved_dtype):
     new_state = back_rotate(rot, moved, p_t, state)
     for key in ("lo", "hi", "edges", "counts_t", "counts_r", "lut"):
         trace[key] = np.asarray(trace[key])
-    trace["moved"] = moved
-    trace["state"] = new_state
+    if keep_arrays:
+        trace["moved"] = moved
+        trace["state"] = new_state
+    else:
+        del trace["proj_t"]
     return new_state, trace
 
 
-def idt_instrumented(target, reference, bins=255, n_iter=4, rotations=None):
+def idt_instrumented(target, reference, bins=255, n_iter=4, rotations=None, keep_arrays=True):
     """IDT that also returns the per-iteration traces.  ``rotations`` (n_iter x 3 x 3)
     replaces the RNG draws when given (used when the matrices were pre-drawn)."""
     hw3 = target.shape
@@ -203,11 +207,11 @@ def idt_instrumented(target, reference, bins=255, n_iter=4, rotations=None):
         rot = draw_rotation(hw3[-1]) if rotations is None else np.asarray(rotations[it])
         # the reference allocates the remapped values with the dtype of the CURRENT
         # state: float32 in iteration 0 for float32 input, float64 afterwards.
-        state, tr = idt_iteration(state, ref, rot, bins, state.dtype)
+        state, tr = idt_iteration(state, ref, rot, bins, state.dtype, keep_arrays)
         traces.append(tr)
     return state.reshape(hw3), traces
 
 
-def iterative_distribution_transfer(target, reference, bins=255, n_iter=4):
+def iterative_distribution_transfer(target, reference, bins=255, n_iter=4, rotations=None):
     """Pitie, Kokaram & Dahyot 2007.  ref: methods/iterative.py:8-59."""
-    return idt_instrumented(target, reference, bins, n_iter)[0]
+    return idt_instrumented(target, reference, bins, n_iter, rotations, keep_arrays=False)[0]
