@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--stress", action="store_true", help="i.i.d. uniform frames instead of the smooth field")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--kernels-only", action="store_true", help="profiling aid: only the timed device steps")
     return ap.parse_args()
 
 
@@ -288,6 +289,11 @@ def main():
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / a.steps
     value = world * F * npix / 1e6 / (ms_step / 1e3)
+    if a.kernels_only:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "Mpix/s", "ms_per_step": ms_step,
+                              "gpu_launches": int(launches), "note": "kernels-only profiling run"}))
+        return
 
     # ---- per-kernel breakdown with CUDA events (stage API == the same kernels, unfused LUT off)
     stages = device.IdtStages(tgt, ref, my_rot, BINS, N_ITER, handle=handle)

@@ -25,7 +25,6 @@ def pinned_empty(shape, dtype):
     t = torch.empty(tuple(shape), dtype={np.dtype(np.float32): torch.float32,
                                          np.dtype(np.float64): torch.float64}[np.dtype(dtype)]).pin_memory()
     a = t.numpy()
-    a.flags.writeable = True
     return a
 
 

@@ -183,8 +183,13 @@ def test_idt_constant_target(api):
     np.random.seed(9)
     ref = oracle.iterative_distribution_transfer(t, r)
     np.random.seed(9)
-    out = it.iterative_distribution_transfer(t, r)
-    _close(out, ref, tol=1e-10)
+    trace = {}
+    out = it.iterative_distribution_transfer(t, r, trace=trace)
+    np.random.seed(9)
+    _check_idt_trace(trace, oracle.idt_instrumented(t, r)[1])
+    # all mass in one bin makes the table ~255x steeper than the identity per iteration, which
+    # amplifies the 1e-16 difference between LAPACK's solve and r^T d: still far inside 1e-4
+    _close(out, ref, tol=1e-6)
 
 
 def test_pair0964_all_methods(api, pair0964, golden):
