@@ -71,34 +71,47 @@ struct PixelIO {
         }
     }
 
-    // group g covers pixels [g*G, g*G+G); caller guarantees the group is complete
+    // The raw vectors of one group: pixels [g*G, g*G+G).  Kept packed (12 registers) so that a
+    // kernel can have the next group's loads in flight while it works on the current one.
+    struct Raw {
+        T e[3 * G];
+    };
     template <bool VEC>
-    __device__ __forceinline__ static void load(const T *img, int64_t plane, int64_t g,
-                                                double (&x)[G][3]) {
-        if (!VEC) {
+    __device__ __forceinline__ static Raw load_raw(const T *img, int64_t plane, int g) {
+        Raw r;
+        if (VEC) {
+            if (LAYOUT == CT_HWC) {
+                const V *v = reinterpret_cast<const V *>(img) + 3 * (int64_t)g;
 #pragma unroll
-            for (int i = 0; i < G; ++i) load1(img, plane, g * G + i, x[i]);
-            return;
-        }
-        T raw[3 * G];
-        if (LAYOUT == CT_HWC) {
-            const V *v = reinterpret_cast<const V *>(img) + 3 * g;
+                for (int k = 0; k < 3; ++k) *reinterpret_cast<V *>(&r.e[k * G]) = v[k];
+            } else {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) *reinterpret_cast<V *>(&raw[k * G]) = v[k];
-#pragma unroll
-            for (int i = 0; i < G; ++i)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) x[i][c] = (double)raw[3 * i + c];
+                for (int c = 0; c < 3; ++c)
+                    *reinterpret_cast<V *>(&r.e[c * G]) = *(reinterpret_cast<const V *>(img + c * plane) + g);
+            }
         } else {
+            if (LAYOUT == CT_HWC) {
+                const T *q = img + 3 * G * (int64_t)g;
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                *reinterpret_cast<V *>(&raw[c * G]) =
-                    *(reinterpret_cast<const V *>(img + c * plane) + g);
+                for (int k = 0; k < 3 * G; ++k) r.e[k] = q[k];
+            } else {
 #pragma unroll
-            for (int i = 0; i < G; ++i)
+                for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) x[i][c] = (double)raw[c * G + i];
+                    for (int i = 0; i < G; ++i) r.e[c * G + i] = img[c * plane + (int64_t)g * G + i];
+            }
         }
+        return r;
+    }
+    __device__ __forceinline__ static void unpack(const Raw &r, double (&x)[G][3]) {
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) x[i][c] = (double)(LAYOUT == CT_HWC ? r.e[3 * i + c] : r.e[c * G + i]);
+    }
+    template <bool VEC>
+    __device__ __forceinline__ static void load(const T *img, int64_t plane, int64_t g, double (&x)[G][3]) {
+        unpack(load_raw<VEC>(img, plane, (int)g), x);
     }
 
     // store GS pixels starting at pixel p0 (GS is the SOURCE group size; p0 % GS == 0)

@@ -32,28 +32,27 @@ __device__ __forceinline__ AxisGrid grid_from_keys(const int64_t *keys, int j, i
     return g;
 }
 
+// np.linspace(lo, hi, bins + 1)[k]
 __device__ __forceinline__ double edge(const AxisGrid &g, int k, int bins) {
     return k >= bins ? g.hi : add_rn(mul_rn((double)k, g.step), g.lo);
 }
 
-// Unique k in [0, bins-1] with edges[k] <= x < edges[k+1] (last bin closed); x in [lo, hi].
-// Also returns edges[k].
-__device__ __forceinline__ int bin_of(const AxisGrid &g, int bins, double x, double &e_lo) {
-    int k = (int)((x - g.lo) * g.inv);
-    k = k < 0 ? 0 : (k > bins - 1 ? bins - 1 : k);
-    double e0 = edge(g, k, bins);
-    if (x < e0) {
-        --k;
-        e0 = edge(g, k, bins);
-    } else if (k != bins - 1) {
-        const double e1 = edge(g, k + 1, bins);
-        if (x >= e1) {
-            ++k;
-            e0 = e1;
-        }
-    }
-    e_lo = e0;
-    return k;
+// Adding 2^52 + 2^51 leaves round-to-nearest(t) in the low mantissa word: no F2I / I2F.
+constexpr double kMagic = 6755399441055744.0;
+
+// Nearest-integer estimate k' of (p - lo) / step, clamped to [0, bins] so that edges[k'] is a
+// valid table read.  The sample's bin is k' - (p < edges[k']), see bin_from.
+__device__ __forceinline__ int bin_estimate(double p, double lo, double inv, int bins) {
+    const double u = fma(p - lo, inv, kMagic);
+    return (int)min((unsigned)__double2loint(u), (unsigned)bins);
+}
+// Unique k in [0, bins-1] with edges[k] <= p < edges[k+1] (last bin closed) from the estimate
+// and the exact table value e = edges[k'].  The estimate is within 1/2 of the true quotient, so
+// the answer is k' or k' - 1 and one comparison against the exact edge decides - the same
+// invariant np.histogram enforces with its -1/+1 correction.
+__device__ __forceinline__ int bin_from(int kest, double p, double e, int bins) {
+    const int k = kest - (p < e ? 1 : 0);
+    return (int)min((unsigned)k, (unsigned)(bins - 1));
 }
 
 __device__ __forceinline__ bool not_finite(double p) {
@@ -110,20 +109,28 @@ struct RangesArgs {
 
 template <typename IO, bool VEC>
 __device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const double *rot,
-                                             int64_t first_block, int64_t nblocks, double (&mn)[6], bool &bad) {
+                                             int first_block, int nblocks, double (&mn)[6], bool &bad) {
     using T = typename IO::elem_t;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
     constexpr int G = IO::G;
-    const int64_t ngroups = im.npix / G;
-    const int64_t stride = nblocks * kThreads;
-    for (int64_t g = first_block * kThreads + threadIdx.x; g < ngroups; g += stride) {
+    const int ngroups = (int)(im.npix / G);
+    const int stride = nblocks * kThreads;
+    int g = first_block * kThreads + threadIdx.x;
+    typename IO::Raw raw{};
+    if (g < ngroups) raw = IO::template load_raw<VEC>(base, im.plane_stride, g);
+    while (g < ngroups) {
+        const int gn = g + stride;
+        typename IO::Raw nxt{};
+        if (gn < ngroups) nxt = IO::template load_raw<VEC>(base, im.plane_stride, gn);  // in flight during the math
         double x[G][3];
-        IO::template load<VEC>(base, im.plane_stride, g, x);
+        IO::unpack(raw, x);
 #pragma unroll
         for (int i = 0; i < G; ++i) track_range(rot, x[i], mn, bad);
+        raw = nxt;
+        g = gn;
     }
     if (first_block == 0 && threadIdx.x == 0) {
-        for (int64_t p = ngroups * G; p < im.npix; ++p) {
+        for (int64_t p = (int64_t)ngroups * G; p < im.npix; ++p) {
             double x[3];
             IO::load1(base, im.plane_stride, p, x);
             track_range(rot, x, mn, bad);
@@ -131,7 +138,7 @@ __device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const 
     }
 }
 
-__global__ void __launch_bounds__(kThreads) ranges_kernel(RangesArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) ranges_kernel(RangesArgs a) {
     const int64_t pair = blockIdx.y;
     __shared__ double rot[9];
     __shared__ double red[kWarps][6];
@@ -153,12 +160,20 @@ __global__ void __launch_bounds__(kThreads) ranges_kernel(RangesArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 // K6: CDFs and inverse-CDF table of one pair, run by one whole block (iterative.py:45-51)
+//
+// LUT block of one pair (CT_IDT_LUT_DOUBLES(bins) doubles), per axis j:
+//   edges[bins+1]                      np.linspace(lo, hi, bins+1)
+//   entry[bins+1][3] = {xp, fp, slope} what np.interp(x, edges[1:], f, left=0) needs for a sample
+//                      whose bin index (before folding x == hi into the last bin) is k:
+//                      k = 0 -> {0,0,0} (left=0), 1 <= k < bins -> {edges[k], f[k-1], slope[k-1]},
+//                      k = bins (x == hi) -> {hi, f[bins-1], 0};  m = slope*(x - xp) + fp.
+// then {lo, hi, step, inv} per axis.
 // ---------------------------------------------------------------------------------------------
 struct LutArgs {
     const int64_t *keys;
     int64_t keys_stride;
     uint64_t *counts;  // [B][2][3][bins]
-    double *lut;       // [B][3*(2*bins+4)]
+    double *lut;
     int32_t *status;
     int bins;
     int keep_counts;
@@ -179,7 +194,6 @@ __device__ void build_lut(const LutArgs &a, int64_t pair, double *sm) {
         bool finite;
         const AxisGrid g = grid_from_keys(a.keys + pair * a.keys_stride, j, bins, finite);
         if (!finite && a.status && threadIdx.x == 0) a.status[pair] = CT_E_NONFINITE;
-        // integer counts -> running sums kept as doubles (exact below 2^53), one thread per image
         for (int k = threadIdx.x; k < bins; k += kThreads) {
             const uint64_t ct_ = __ldcg(cnt + (0 * 3 + j) * bins + k);
             const uint64_t cr = __ldcg(cnt + (1 * 3 + j) * bins + k);
@@ -189,7 +203,7 @@ __device__ void build_lut(const LutArgs &a, int64_t pair, double *sm) {
             if (a.tr_cr) a.tr_cr[(tr_base + j) * bins + k] = (int64_t)cr;
         }
         __syncthreads();
-        if (threadIdx.x < 2) {  // p.cumsum().astype(float); cp /= cp[-1]
+        if (threadIdx.x < 2) {  // p.cumsum().astype(float); cp /= cp[-1]  (integers < 2^53: exact)
             double *c = threadIdx.x == 0 ? cdf_t : cdf_r;
             double run = 0.0;
             for (int k = 0; k < bins; ++k) {
@@ -222,15 +236,26 @@ __device__ void build_lut(const LutArgs &a, int64_t pair, double *sm) {
             f[i] = v;
         }
         __syncthreads();
-        double *lf = lut + j * 2 * bins, *ls = lf + bins;
-        for (int i = threadIdx.x; i < bins; i += kThreads) {
-            lf[i] = f[i];
-            // slopes of np.interp(x, edges[1:], f): (f[i+1]-f[i]) / (edges[i+2]-edges[i+1])
-            ls[i] = i < bins - 1 ? div_rn(sub_rn(f[i + 1], f[i]), sub_rn(edge(g, i + 2, bins), edge(g, i + 1, bins))) : 0.0;
-            if (a.tr_lut) a.tr_lut[(tr_base + j) * bins + i] = f[i];
+        double *le = lut + (int64_t)j * 4 * (bins + 1), *lt = le + (bins + 1);
+        for (int k = threadIdx.x; k <= bins; k += kThreads) {
+            le[k] = edge(g, k, bins);
+            double xp = 0.0, fp = 0.0, sl = 0.0;
+            if (k == bins) {
+                xp = g.hi;
+                fp = f[bins - 1];
+            } else if (k >= 1) {
+                xp = edge(g, k, bins);
+                fp = f[k - 1];
+                // slopes of np.interp(x, edges[1:], f): (f[i+1]-f[i]) / (edges[i+2]-edges[i+1]), i = k-1
+                sl = div_rn(sub_rn(f[k], f[k - 1]), sub_rn(edge(g, k + 1, bins), xp));
+            }
+            lt[3 * k + 0] = xp;
+            lt[3 * k + 1] = fp;
+            lt[3 * k + 2] = sl;
+            if (a.tr_lut && k < bins) a.tr_lut[(tr_base + j) * bins + k] = f[k];
         }
         if (threadIdx.x == 0) {
-            double *tail = lut + 3 * 2 * bins + 4 * j;
+            double *tail = lut + (int64_t)12 * (bins + 1) + 4 * j;
             tail[0] = g.lo; tail[1] = g.hi; tail[2] = g.step; tail[3] = g.inv;
             if (a.tr_lo) a.tr_lo[tr_base + j] = g.lo;
             if (a.tr_hi) a.tr_hi[tr_base + j] = g.hi;
@@ -251,6 +276,7 @@ __global__ void __launch_bounds__(kThreads) lut_kernel(LutArgs a) {
 // Each block serves one image of one pair.  The block's three 1-D histograms are replicated
 // R times, copy = lane % R, copies interleaved (index = bin*R + copy) so that the lanes of a
 // warp that hit the same or neighbouring bins (smooth images) land in different banks.
+// The exact edges of the three axes sit in shared memory next to them.
 // ---------------------------------------------------------------------------------------------
 struct HistArgs {
     Img img[2];
@@ -269,36 +295,57 @@ struct HistArgs {
     LutArgs lut;
 };
 
+struct HistShared {
+    double rot[18];
+    AxisGrid grid[3];
+    double red[kWarps][6];
+    bool is_last;
+};
+
 template <typename IO, bool VEC, bool NEXT>
-__device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const double *rot, const double *rot_next,
-                                           const AxisGrid *grid, int bins, int copies_log2, unsigned int *hist,
-                                           int64_t first_block, int64_t nblocks, double (&mn)[6], bool &bad) {
+__device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const HistShared &sh, const double *edges,
+                                           int bins, int copies_log2, unsigned int *hist, int first_block,
+                                           int nblocks, double (&mn)[6], bool &bad) {
     using T = typename IO::elem_t;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
     constexpr int G = IO::G;
-    const int64_t ngroups = im.npix / G;
-    const int64_t stride = nblocks * kThreads;
+    const int ngroups = (int)(im.npix / G);
+    const int stride = nblocks * kThreads;
     const int copy = threadIdx.x & ((1 << copies_log2) - 1);
+    double r[9], lo[3], inv[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r[i] = sh.rot[i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        lo[j] = sh.grid[j].lo;
+        inv[j] = sh.grid[j].inv;
+    }
     auto one = [&](const double(&x)[3]) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            const double p = dot3(rot + 3 * j, x);
-            if (p >= grid[j].lo && p <= grid[j].hi) {  // np.histogram's `keep`
-                double e;
-                const int k = bin_of(grid[j], bins, p, e);
-                atomicAdd(&hist[((j * bins + k) << copies_log2) + copy], 1u);
-            }
+            const double p = dot3(r + 3 * j, x);
+            const int ke = bin_estimate(p, lo[j], inv[j], bins);
+            const int k = bin_from(ke, p, edges[j * (bins + 1) + ke], bins);
+            atomicAdd(&hist[((j * bins + k) << copies_log2) + copy], 1u);
         }
-        if (NEXT) track_range(rot_next, x, mn, bad);
+        if (NEXT) track_range(sh.rot + 9, x, mn, bad);
     };
-    for (int64_t g = first_block * kThreads + threadIdx.x; g < ngroups; g += stride) {
+    int g = first_block * kThreads + threadIdx.x;
+    typename IO::Raw raw{};
+    if (g < ngroups) raw = IO::template load_raw<VEC>(base, im.plane_stride, g);
+    while (g < ngroups) {
+        const int gn = g + stride;
+        typename IO::Raw nxt{};
+        if (gn < ngroups) nxt = IO::template load_raw<VEC>(base, im.plane_stride, gn);  // in flight during the math
         double x[G][3];
-        IO::template load<VEC>(base, im.plane_stride, g, x);
+        IO::unpack(raw, x);
 #pragma unroll
         for (int i = 0; i < G; ++i) one(x[i]);
+        raw = nxt;
+        g = gn;
     }
     if (first_block == 0 && threadIdx.x == 0) {
-        for (int64_t p = ngroups * G; p < im.npix; ++p) {
+        for (int64_t p = (int64_t)ngroups * G; p < im.npix; ++p) {
             double x[3];
             IO::load1(base, im.plane_stride, p, x);
             one(x);
@@ -306,27 +353,30 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const do
     }
 }
 
-__global__ void __launch_bounds__(kThreads) hist_kernel(HistArgs a) {
-    extern __shared__ double sm_dyn[];  // histograms, later reused by the LUT build
-    unsigned int *hist = reinterpret_cast<unsigned int *>(sm_dyn);
-    __shared__ double rot[18];
-    __shared__ AxisGrid grid[3];
-    __shared__ double red[kWarps][6];
-    __shared__ bool is_last;
+__global__ void __launch_bounds__(kThreads, 2) hist_kernel(HistArgs a) {
+    extern __shared__ double sm_dyn[];  // edges[3][bins+1], histograms; later reused by the LUT build
+    __shared__ HistShared sh;
     const int64_t pair = blockIdx.y;
     const int bins = a.bins;
-    const int z = blockIdx.x < a.nblk[0] ? 0 : 1;
-    const int64_t first_block = z == 0 ? blockIdx.x : blockIdx.x - a.nblk[0];
+    double *edges = sm_dyn;
+    unsigned int *hist = reinterpret_cast<unsigned int *>(sm_dyn + 3 * (bins + 1));
+    const int z = (int)blockIdx.x < a.nblk[0] ? 0 : 1;
+    const int first_block = z == 0 ? blockIdx.x : blockIdx.x - a.nblk[0];
     const bool next = (z == 1) && a.rot_next != nullptr && a.keys_next != nullptr;
 
-    if (threadIdx.x < 9) rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
-    else if (threadIdx.x < 18 && next) rot[threadIdx.x] = a.rot_next[pair * a.rot_stride + threadIdx.x - 9];
+    if (threadIdx.x < 9) sh.rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
+    else if (threadIdx.x < 18 && next) sh.rot[threadIdx.x] = a.rot_next[pair * a.rot_stride + threadIdx.x - 9];
     if (threadIdx.x >= 32 && threadIdx.x < 35) {
         bool finite;
-        grid[threadIdx.x - 32] = grid_from_keys(a.keys + pair * a.keys_stride, threadIdx.x - 32, bins, finite);
+        sh.grid[threadIdx.x - 32] = grid_from_keys(a.keys + pair * a.keys_stride, threadIdx.x - 32, bins, finite);
     }
     const int nslots = (3 * bins) << a.copies_log2;
     for (int i = threadIdx.x; i < nslots; i += kThreads) hist[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * (bins + 1); i += kThreads) {
+        const int j = i / (bins + 1);
+        edges[i] = edge(sh.grid[j], i - j * (bins + 1), bins);
+    }
     __syncthreads();
 
     double mn[6];
@@ -336,17 +386,17 @@ __global__ void __launch_bounds__(kThreads) hist_kernel(HistArgs a) {
     const int sel = a.kind[z] * 2 + a.vec[z];
     if (next) {
         switch (sel) {
-#define CT_CASE(ID, T, L, V)                                                                              \
-    case ID: hist_image<PixelIO<T, L>, V, true>(a.img[z], pair, rot, rot + 9, grid, bins, a.copies_log2,  \
-                                                hist, first_block, a.nblk[z], mn, bad); break;
+#define CT_CASE(ID, T, L, V)                                                                          \
+    case ID: hist_image<PixelIO<T, L>, V, true>(a.img[z], pair, sh, edges, bins, a.copies_log2, hist, \
+                                                first_block, a.nblk[z], mn, bad); break;
             CT_FOR_EACH_SRC(CT_CASE)
 #undef CT_CASE
         }
     } else {
         switch (sel) {
-#define CT_CASE(ID, T, L, V)                                                                              \
-    case ID: hist_image<PixelIO<T, L>, V, false>(a.img[z], pair, rot, rot + 9, grid, bins, a.copies_log2, \
-                                                 hist, first_block, a.nblk[z], mn, bad); break;
+#define CT_CASE(ID, T, L, V)                                                                           \
+    case ID: hist_image<PixelIO<T, L>, V, false>(a.img[z], pair, sh, edges, bins, a.copies_log2, hist, \
+                                                 first_block, a.nblk[z], mn, bad); break;
             CT_FOR_EACH_SRC(CT_CASE)
 #undef CT_CASE
         }
@@ -361,7 +411,7 @@ __global__ void __launch_bounds__(kThreads) hist_kernel(HistArgs a) {
         if (s) atomicAdd(reinterpret_cast<unsigned long long *>(cnt + i), (unsigned long long)s);
     }
     if (next) {
-        fold_range(mn, a.keys_next + pair * a.keys_stride, red);
+        fold_range(mn, a.keys_next + pair * a.keys_stride, sh.red);
         if (a.status && __syncthreads_or(bad) && threadIdx.x == 0) a.status[pair] = CT_E_NONFINITE;
     }
     if (!a.fuse_lut) return;
@@ -369,11 +419,11 @@ __global__ void __launch_bounds__(kThreads) hist_kernel(HistArgs a) {
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int t = atomicAdd(&a.tickets[pair], 1u);
-        is_last = (t == gridDim.x - 1u);
-        if (is_last) a.tickets[pair] = 0;
+        sh.is_last = (t == gridDim.x - 1u);
+        if (sh.is_last) a.tickets[pair] = 0;
     }
     __syncthreads();
-    if (!is_last) return;
+    if (!sh.is_last) return;
     __threadfence();
     build_lut(a.lut, pair, sm_dyn);
 }
@@ -396,47 +446,67 @@ struct RemapArgs {
     int round_f32;
 };
 
-template <typename SIO, typename DIO, bool VEC, bool NEXT>
-__device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, const double *rot, const double *rot_next,
-                                            const AxisGrid *grid, const double *lut, double (&mn)[6], bool &bad) {
+struct RemapShared {
+    double rot[18];
+    AxisGrid grid[3];
+    double red[kWarps][6];
+};
+
+template <typename SIO, typename DIO, bool VEC, bool NEXT, bool ROUND32>
+__device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, const RemapShared &sh,
+                                            const double *tab, double (&mn)[6], bool &bad) {
     using TS = typename SIO::elem_t;
     const TS *src = reinterpret_cast<const TS *>(a.src.data) + pair * a.src.image_stride;
     double *dst = reinterpret_cast<double *>(a.dst.data) + pair * a.dst.image_stride;
     constexpr int G = SIO::G;
     const int bins = a.bins;
-    const bool round_f32 = a.round_f32 != 0;
-    const int64_t ngroups = a.src.npix / G;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    const int ngroups = (int)(a.src.npix / G);
+    const int stride = (int)gridDim.x * kThreads;
+    double r[9], lo[3], inv[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r[i] = sh.rot[i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        lo[j] = sh.grid[j].lo;
+        inv[j] = sh.grid[j].inv;
+    }
     auto one = [&](const double(&x)[3], double(&y)[3]) {
         double d[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-            const double p = dot3(rot + 3 * j, x);
-            const double *f = lut + j * 2 * bins, *sl = f + bins;
-            double e;
-            const int k = bin_of(grid[j], bins, p, e);
-            double m;
-            if (p >= grid[j].hi) m = f[bins - 1];   // x == xp[-1]
-            else if (k == 0) m = 0.0;                // x < edges[1]: np.interp(..., left=0)
-            else m = add_rn(mul_rn(sl[k - 1], sub_rn(p, e)), f[k - 1]);
-            if (round_f32) m = (double)(float)m;     // float32 d_r buffer, iterative.py:36
+            const double p = dot3(r + 3 * j, x);
+            const double *edges = tab + j * 4 * (bins + 1), *ent = edges + (bins + 1);
+            const int ke = bin_estimate(p, lo[j], inv[j], bins);
+            // bin index BEFORE folding p == hi into the last bin: ke - (p < edges[ke]) in [0, bins]
+            const int k = (int)min((unsigned)(ke - (p < edges[ke] ? 1 : 0)), (unsigned)bins);
+            const double xp = ent[3 * k], fp = ent[3 * k + 1], sl = ent[3 * k + 2];
+            double m = add_rn(mul_rn(sl, sub_rn(p, xp)), fp);   // np.interp: slope*(x - xp[j]) + fp[j]
+            if (ROUND32) m = (double)(float)m;                  // float32 d_r buffer, iterative.py:36
             d[j] = sub_rn(m, p);
         }
         // solve(r, d) for orthogonal r is r^T d; then "+ target"
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-            y[c] = add_rn(fma(rot[6 + c], d[2], fma(rot[3 + c], d[1], mul_rn(rot[c], d[0]))), x[c]);
-        if (NEXT) track_range(rot_next, y, mn, bad);
+            y[c] = add_rn(fma(r[6 + c], d[2], fma(r[3 + c], d[1], mul_rn(r[c], d[0]))), x[c]);
+        if (NEXT) track_range(sh.rot + 9, y, mn, bad);
     };
-    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += stride) {
+    int g = (int)blockIdx.x * kThreads + threadIdx.x;
+    typename SIO::Raw raw{};
+    if (g < ngroups) raw = SIO::template load_raw<VEC>(src, a.src.plane_stride, g);
+    while (g < ngroups) {
+        const int gn = g + stride;
+        typename SIO::Raw nxt{};
+        if (gn < ngroups) nxt = SIO::template load_raw<VEC>(src, a.src.plane_stride, gn);  // in flight during the math
         double x[G][3], y[G][3];
-        SIO::template load<VEC>(src, a.src.plane_stride, g, x);
+        SIO::unpack(raw, x);
 #pragma unroll
         for (int i = 0; i < G; ++i) one(x[i], y[i]);
-        DIO::template store<VEC, G>(dst, a.dst.plane_stride, g * G, y);
+        DIO::template store<VEC, G>(dst, a.dst.plane_stride, (int64_t)g * G, y);
+        raw = nxt;
+        g = gn;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int64_t p = ngroups * G; p < a.src.npix; ++p) {
+        for (int64_t p = (int64_t)ngroups * G; p < a.src.npix; ++p) {
             double x[3], y[3];
             SIO::load1(src, a.src.plane_stride, p, x);
             one(x, y);
@@ -445,50 +515,54 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
     }
 }
 
-__global__ void __launch_bounds__(kThreads) remap_kernel(RemapArgs a) {
-    extern __shared__ double sm_tab[];  // f and slope of the three axes
-    __shared__ double rot[18];
-    __shared__ AxisGrid grid[3];
-    __shared__ double red[kWarps][6];
+// one instantiation per (source kind, vectorised); destination layout, NEXT and ROUND32 are
+// block-uniform runtime switches inside
+template <typename SIO, bool VEC>
+__device__ __forceinline__ void remap_dispatch(const RemapArgs &a, int64_t pair, const RemapShared &sh,
+                                               const double *tab, bool next, double (&mn)[6], bool &bad) {
+    using StateIO = PixelIO<double, CT_CHW>;
+    using FinalIO = PixelIO<double, CT_HWC>;
+    if (a.round_f32) {  // iteration 0 of float32 input: the state buffer is always the destination or n_iter == 1
+        if (a.dst_layout == CT_CHW) {
+            if (next) remap_image<SIO, StateIO, VEC, true, true>(a, pair, sh, tab, mn, bad);
+            else remap_image<SIO, StateIO, VEC, false, true>(a, pair, sh, tab, mn, bad);
+        } else {
+            if (next) remap_image<SIO, FinalIO, VEC, true, true>(a, pair, sh, tab, mn, bad);
+            else remap_image<SIO, FinalIO, VEC, false, true>(a, pair, sh, tab, mn, bad);
+        }
+    } else if (a.dst_layout == CT_CHW) {
+        if (next) remap_image<SIO, StateIO, VEC, true, false>(a, pair, sh, tab, mn, bad);
+        else remap_image<SIO, StateIO, VEC, false, false>(a, pair, sh, tab, mn, bad);
+    } else {
+        if (next) remap_image<SIO, FinalIO, VEC, true, false>(a, pair, sh, tab, mn, bad);
+        else remap_image<SIO, FinalIO, VEC, false, false>(a, pair, sh, tab, mn, bad);
+    }
+}
+
+template <typename SIO, bool VEC>
+__global__ void __launch_bounds__(kThreads, 2) remap_kernel(RemapArgs a) {
+    extern __shared__ double sm_tab[];  // edges + {xp, fp, slope} entries of the three axes
+    __shared__ RemapShared sh;
     const int64_t pair = blockIdx.y;
     const int bins = a.bins;
     const bool next = a.rot_next != nullptr && a.keys_next != nullptr;
     const double *lut = a.lut + pair * CT_IDT_LUT_DOUBLES(bins);
-    if (threadIdx.x < 9) rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
-    else if (threadIdx.x < 18 && next) rot[threadIdx.x] = a.rot_next[pair * a.rot_stride + threadIdx.x - 9];
+    if (threadIdx.x < 9) sh.rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
+    else if (threadIdx.x < 18 && next) sh.rot[threadIdx.x] = a.rot_next[pair * a.rot_stride + threadIdx.x - 9];
     if (threadIdx.x >= 32 && threadIdx.x < 35) {
-        const double *tail = lut + 6 * bins + 4 * (threadIdx.x - 32);
-        grid[threadIdx.x - 32] = AxisGrid{tail[0], tail[1], tail[2], tail[3]};
+        const double *tail = lut + 12 * (bins + 1) + 4 * (threadIdx.x - 32);
+        sh.grid[threadIdx.x - 32] = AxisGrid{tail[0], tail[1], tail[2], tail[3]};
     }
-    for (int i = threadIdx.x; i < 6 * bins; i += kThreads) sm_tab[i] = lut[i];
+    for (int i = threadIdx.x; i < 12 * (bins + 1); i += kThreads) sm_tab[i] = lut[i];
     __syncthreads();
 
     double mn[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) mn[i] = INFINITY;
     bool bad = false;
-    const int sel = a.kind * 2 + a.vec;
-#define CT_REMAP_SWITCH(DIO, NEXTV)                                                                      \
-    switch (sel) {                                                                                       \
-        case 0: remap_image<PixelIO<float, CT_HWC>, DIO, false, NEXTV>(a, pair, rot, rot + 9, grid, sm_tab, mn, bad); break;  \
-        case 1: remap_image<PixelIO<float, CT_HWC>, DIO, true, NEXTV>(a, pair, rot, rot + 9, grid, sm_tab, mn, bad); break;   \
-        case 2: remap_image<PixelIO<float, CT_CHW>, DIO, false, NEXTV>(a, pair, rot, rot + 9, grid, sm_tab, mn, bad); break;  \
-        case 3: remap_image<PixelIO<float, CT_CHW>, DIO, true, NEXTV>(a, pair, rot, rot + 9, grid, sm_tab, mn, bad); break;   \
-        case 4: remap_image<PixelIO<double, CT_HWC>, DIO, false, NEXTV>(a, pair, rot, rot + 9, grid, sm_tab, mn, bad); break; \
-        case 5: remap_image<PixelIO<double, CT_HWC>, DIO, true, NEXTV>(a, pair, rot, rot + 9, grid, sm_tab, mn, bad); break;  \
-        case 6: remap_image<PixelIO<double, CT_CHW>, DIO, false, NEXTV>(a, pair, rot, rot + 9, grid, sm_tab, mn, bad); break; \
-        case 7: remap_image<PixelIO<double, CT_CHW>, DIO, true, NEXTV>(a, pair, rot, rot + 9, grid, sm_tab, mn, bad); break;  \
-    }
-    using StateIO = PixelIO<double, CT_CHW>;
-    using FinalIO = PixelIO<double, CT_HWC>;
-    if (a.dst_layout == CT_CHW) {
-        if (next) { CT_REMAP_SWITCH(StateIO, true) } else { CT_REMAP_SWITCH(StateIO, false) }
-    } else {
-        if (next) { CT_REMAP_SWITCH(FinalIO, true) } else { CT_REMAP_SWITCH(FinalIO, false) }
-    }
-#undef CT_REMAP_SWITCH
+    remap_dispatch<SIO, VEC>(a, pair, sh, sm_tab, next, mn, bad);
     if (next) {
-        fold_range(mn, a.keys_next + pair * a.keys_stride, red);
+        fold_range(mn, a.keys_next + pair * a.keys_stride, sh.red);
         if (a.status && __syncthreads_or(bad) && threadIdx.x == 0) a.status[pair] = CT_E_NONFINITE;
     }
 }
@@ -549,7 +623,7 @@ static LutArgs lut_args(const ct_idt_stage *s, int keep_counts, const ct_idt_tra
     return l;
 }
 
-static int copies_log2_for(int bins) { return bins <= 256 ? 3 : (bins <= 512 ? 2 : 1); }
+static int copies_log2_for(int bins) { return bins <= 256 ? 3 : (bins <= 512 ? 2 : 0); }
 
 int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt_trace *trace,
                 int trace_iter, int trace_niter) {
@@ -595,9 +669,8 @@ int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt
     CT_TRY(ensure_scratch(h, B));
     a.tickets = h->tickets;
     a.lut = lut_args(s, 0, trace, trace_iter, trace_niter);
-    size_t smem = (size_t)((3 * s->bins) << a.copies_log2) * sizeof(unsigned int);
-    const size_t lut_smem = (size_t)3 * s->bins * sizeof(double);
-    if (fuse_lut && lut_smem > smem) smem = lut_smem;
+    const size_t smem = (size_t)3 * (s->bins + 1) * sizeof(double) +
+                        (size_t)((3 * s->bins) << a.copies_log2) * sizeof(unsigned int);  // >= 3*bins doubles for the LUT build
     hist_kernel<<<dim3(a.nblk[0] + a.nblk[1], B), kThreads, smem, h->stream>>>(a);
     h->launches++;
     CT_CUDA(h, cudaGetLastError());
@@ -638,15 +711,22 @@ int launch_remap(ct_context *h, const ct_idt_stage *s, const ct_batch *dst, int 
     a.status = s->status;
     a.bins = s->bins;
     a.round_f32 = round_f32;
-    const int nblk = stream_blocks(h, s->target->npix, s->target->count, 8);
-    if ((size_t)6 * s->bins * sizeof(double) > 40 * 1024) {  // above the default 48 KB with the static part
-        if (!h->remap_smem_raised) {
-            CT_CUDA(h, cudaFuncSetAttribute(remap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            6 * CT_IDT_MAX_BINS * (int)sizeof(double)));
-            h->remap_smem_raised = true;
-        }
+    const int nblk = stream_blocks(h, s->target->npix, s->target->count, 6);
+    const size_t smem = (size_t)12 * (s->bins + 1) * sizeof(double);
+    const dim3 grid(nblk, s->target->count);
+    switch (a.kind * 2 + a.vec) {
+#define CT_CASE(ID, T, L, V)                                                                                   \
+    case ID:                                                                                                   \
+        if (smem > 40 * 1024 && !h->remap_smem_raised[ID]) {                                                   \
+            CT_CUDA(h, cudaFuncSetAttribute(remap_kernel<PixelIO<T, L>, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            12 * (CT_IDT_MAX_BINS + 1) * (int)sizeof(double)));                \
+            h->remap_smem_raised[ID] = true;                                                                   \
+        }                                                                                                      \
+        remap_kernel<PixelIO<T, L>, V><<<grid, kThreads, smem, h->stream>>>(a);                                \
+        break;
+        CT_FOR_EACH_SRC(CT_CASE)
+#undef CT_CASE
     }
-    remap_kernel<<<dim3(nblk, s->target->count), kThreads, (size_t)6 * s->bins * sizeof(double), h->stream>>>(a);
     h->launches++;
     CT_CUDA(h, cudaGetLastError());
     return CT_OK;

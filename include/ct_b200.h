@@ -113,8 +113,9 @@ int ct_linear_transfer_host(ct_handle h, int method, const ct_batch *target,
 /* ------------------------------------------------------------------ IDT (iterative.py:8-59) */
 #define CT_IDT_MAX_BINS 1024
 #define CT_IDT_KEYS 6 /* per pair and iteration: monotone int64 keys of lo[3], -hi[3] */
-/* doubles per pair in a LUT block: f[bins], slope[bins], then lo,hi,step,inv per axis */
-#define CT_IDT_LUT_DOUBLES(bins) (3 * (2 * (int64_t)(bins) + 4))
+/* doubles per pair in a LUT block: per axis edges[bins+1] and {xp,fp,slope}[bins+1], then
+ * lo,hi,step,inv per axis (layout documented at K6 in csrc/ct_idt.cu) */
+#define CT_IDT_LUT_DOUBLES(bins) (3 * (4 * ((int64_t)(bins) + 1) + 4))
 
 typedef struct ct_idt_stage {
     const ct_batch *target;    /* current target state (the input images on iteration 0)   */
