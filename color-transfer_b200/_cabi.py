@@ -25,7 +25,7 @@ CT_IDT_KEYS = 6
 
 
 def lut_doubles(bins):
-    return 3 * (4 * (bins + 1) + 4)
+    return 3 * (3 * ((bins + 2) // 2 * 2) + 4)
 
 
 class Batch(ctypes.Structure):

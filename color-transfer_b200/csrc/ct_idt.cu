@@ -76,13 +76,17 @@ __device__ __forceinline__ void fold_range(double (&mn)[6], int64_t *keys, doubl
     }
 }
 
+// Running minima of (p, -p).  Plain compare-select: fmin()'s NaN handling costs twice as many
+// instructions, and non-finite samples are caught once, by K4 on the inputs (CHECK).
+template <bool CHECK>
 __device__ __forceinline__ void track_range(const double *rot, const double (&x)[3], double (&mn)[6], bool &bad) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const double p = dot3(rot + 3 * j, x);
-        bad |= not_finite(p);
-        mn[j] = fmin(mn[j], p);
-        mn[3 + j] = fmin(mn[3 + j], -p);
+        const double q = -p;
+        if (CHECK) bad |= not_finite(p);
+        mn[j] = p < mn[j] ? p : mn[j];
+        mn[3 + j] = q < mn[3 + j] ? q : mn[3 + j];
     }
 }
 
@@ -125,7 +129,7 @@ __device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const 
         double x[G][3];
         IO::unpack(raw, x);
 #pragma unroll
-        for (int i = 0; i < G; ++i) track_range(rot, x[i], mn, bad);
+        for (int i = 0; i < G; ++i) track_range<true>(rot, x[i], mn, bad);
         raw = nxt;
         g = gn;
     }
@@ -133,7 +137,7 @@ __device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const 
         for (int64_t p = (int64_t)ngroups * G; p < im.npix; ++p) {
             double x[3];
             IO::load1(base, im.plane_stride, p, x);
-            track_range(rot, x, mn, bad);
+            track_range<true>(rot, x, mn, bad);
         }
     }
 }
@@ -162,11 +166,11 @@ __global__ void __launch_bounds__(kThreads, 2) ranges_kernel(RangesArgs a) {
 // K6: CDFs and inverse-CDF table of one pair, run by one whole block (iterative.py:45-51)
 //
 // LUT block of one pair (CT_IDT_LUT_DOUBLES(bins) doubles), per axis j:
-//   edges[bins+1]                      np.linspace(lo, hi, bins+1)
-//   entry[bins+1][3] = {xp, fp, slope} what np.interp(x, edges[1:], f, left=0) needs for a sample
-//                      whose bin index (before folding x == hi into the last bin) is k:
-//                      k = 0 -> {0,0,0} (left=0), 1 <= k < bins -> {edges[k], f[k-1], slope[k-1]},
-//                      k = bins (x == hi) -> {hi, f[bins-1], 0};  m = slope*(x - xp) + fp.
+//   edges[E]              np.linspace(lo, hi, bins+1), E = bins+1 rounded up to even
+//   entry[E][2] = {fp, slope}  what np.interp(x, edges[1:], f, left=0) needs, besides xp = edges[k],
+//                      for a sample whose bin index (before folding x == hi into the last bin) is k:
+//                      k = 0 -> {0,0} (left=0), 1 <= k < bins -> {f[k-1], slope[k-1]},
+//                      k = bins (x == hi) -> {f[bins-1], 0};  m = slope*(x - edges[k]) + fp.
 // then {lo, hi, step, inv} per axis.
 // ---------------------------------------------------------------------------------------------
 struct LutArgs {
@@ -236,7 +240,8 @@ __device__ void build_lut(const LutArgs &a, int64_t pair, double *sm) {
             f[i] = v;
         }
         __syncthreads();
-        double *le = lut + (int64_t)j * 4 * (bins + 1), *lt = le + (bins + 1);
+        const int E = CT_IDT_EDGE_STRIDE(bins);
+        double *le = lut + (int64_t)j * E, *lt = lut + (int64_t)(3 + 2 * j) * E;
         for (int k = threadIdx.x; k <= bins; k += kThreads) {
             le[k] = edge(g, k, bins);
             double xp = 0.0, fp = 0.0, sl = 0.0;
@@ -249,13 +254,12 @@ __device__ void build_lut(const LutArgs &a, int64_t pair, double *sm) {
                 // slopes of np.interp(x, edges[1:], f): (f[i+1]-f[i]) / (edges[i+2]-edges[i+1]), i = k-1
                 sl = div_rn(sub_rn(f[k], f[k - 1]), sub_rn(edge(g, k + 1, bins), xp));
             }
-            lt[3 * k + 0] = xp;
-            lt[3 * k + 1] = fp;
-            lt[3 * k + 2] = sl;
+            lt[2 * k + 0] = fp;
+            lt[2 * k + 1] = sl;
             if (a.tr_lut && k < bins) a.tr_lut[(tr_base + j) * bins + k] = f[k];
         }
         if (threadIdx.x == 0) {
-            double *tail = lut + (int64_t)12 * (bins + 1) + 4 * j;
+            double *tail = lut + (int64_t)9 * CT_IDT_EDGE_STRIDE(bins) + 4 * j;
             tail[0] = g.lo; tail[1] = g.hi; tail[2] = g.step; tail[3] = g.inv;
             if (a.tr_lo) a.tr_lo[tr_base + j] = g.lo;
             if (a.tr_hi) a.tr_hi[tr_base + j] = g.hi;
@@ -302,19 +306,23 @@ struct HistShared {
     bool is_last;
 };
 
-template <typename IO, bool VEC, bool NEXT>
+template <typename IO, bool VEC, bool NEXT, int CL2>  // CL2: log2(copies) when known at compile time, else -1
 __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const HistShared &sh, const double *edges,
-                                           int bins, int copies_log2, unsigned int *hist, int first_block,
+                                           int bins, int copies_log2_rt, unsigned int *hist, int first_block,
                                            int nblocks, double (&mn)[6], bool &bad) {
+    const int copies_log2 = CL2 >= 0 ? CL2 : copies_log2_rt;
     using T = typename IO::elem_t;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
     constexpr int G = IO::G;
     const int ngroups = (int)(im.npix / G);
     const int stride = nblocks * kThreads;
     const int copy = threadIdx.x & ((1 << copies_log2) - 1);
-    double r[9], lo[3], inv[3];
+    double r[9], rn[9], lo[3], inv[3];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) r[i] = sh.rot[i];
+    for (int i = 0; i < 9; ++i) {
+        r[i] = sh.rot[i];
+        rn[i] = NEXT ? sh.rot[9 + i] : 0.0;
+    }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         lo[j] = sh.grid[j].lo;
@@ -325,10 +333,10 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Hi
         for (int j = 0; j < 3; ++j) {
             const double p = dot3(r + 3 * j, x);
             const int ke = bin_estimate(p, lo[j], inv[j], bins);
-            const int k = bin_from(ke, p, edges[j * (bins + 1) + ke], bins);
-            atomicAdd(&hist[((j * bins + k) << copies_log2) + copy], 1u);
+            const int k = bin_from(ke, p, (edges + j * (bins + 1))[ke], bins);
+            atomicAdd(&(hist + ((j * bins) << copies_log2) + copy)[k << copies_log2], 1u);
         }
-        if (NEXT) track_range(sh.rot + 9, x, mn, bad);
+        if (NEXT) track_range<false>(rn, x, mn, bad);
     };
     int g = first_block * kThreads + threadIdx.x;
     typename IO::Raw raw{};
@@ -384,23 +392,23 @@ __global__ void __launch_bounds__(kThreads, 2) hist_kernel(HistArgs a) {
     for (int i = 0; i < 6; ++i) mn[i] = INFINITY;
     bool bad = false;
     const int sel = a.kind[z] * 2 + a.vec[z];
-    if (next) {
-        switch (sel) {
-#define CT_CASE(ID, T, L, V)                                                                          \
-    case ID: hist_image<PixelIO<T, L>, V, true>(a.img[z], pair, sh, edges, bins, a.copies_log2, hist, \
-                                                first_block, a.nblk[z], mn, bad); break;
-            CT_FOR_EACH_SRC(CT_CASE)
-#undef CT_CASE
-        }
-    } else {
-        switch (sel) {
-#define CT_CASE(ID, T, L, V)                                                                           \
-    case ID: hist_image<PixelIO<T, L>, V, false>(a.img[z], pair, sh, edges, bins, a.copies_log2, hist, \
-                                                 first_block, a.nblk[z], mn, bad); break;
-            CT_FOR_EACH_SRC(CT_CASE)
-#undef CT_CASE
-        }
+#define CT_HIST_SWITCH(NEXTV, CL2V)                                                                          \
+    switch (sel) {                                                                                       \
+        CT_FOR_EACH_SRC(CT_CASE_##NEXTV##_##CL2V)                                                        \
     }
+#define CT_HIST_CALL(T, L, V, NEXTV, CL2V)                                                               \
+    hist_image<PixelIO<T, L>, V, NEXTV, CL2V>(a.img[z], pair, sh, edges, bins, a.copies_log2, hist, first_block, a.nblk[z], mn, bad)
+#define CT_CASE_true_3(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, true, 3); break;
+#define CT_CASE_false_3(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, false, 3); break;
+#define CT_CASE_true_g(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, true, -1); break;
+#define CT_CASE_false_g(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, false, -1); break;
+    if (a.copies_log2 == 3) {  // bins <= 256: the default 255
+        if (next) { CT_HIST_SWITCH(true, 3) } else { CT_HIST_SWITCH(false, 3) }
+    } else {
+        if (next) { CT_HIST_SWITCH(true, g) } else { CT_HIST_SWITCH(false, g) }
+    }
+#undef CT_HIST_SWITCH
+#undef CT_HIST_CALL
     __syncthreads();
     // flush: sum the copies of each bin, one 64-bit integer atomic per non-empty bin
     uint64_t *cnt = a.counts + (pair * 2 + z) * 3 * (int64_t)bins;
@@ -410,10 +418,7 @@ __global__ void __launch_bounds__(kThreads, 2) hist_kernel(HistArgs a) {
         for (int c = 0; c < copies; ++c) s += hist[(i << a.copies_log2) + c];
         if (s) atomicAdd(reinterpret_cast<unsigned long long *>(cnt + i), (unsigned long long)s);
     }
-    if (next) {
-        fold_range(mn, a.keys_next + pair * a.keys_stride, sh.red);
-        if (a.status && __syncthreads_or(bad) && threadIdx.x == 0) a.status[pair] = CT_E_NONFINITE;
-    }
+    if (next) fold_range(mn, a.keys_next + pair * a.keys_stride, sh.red);
     if (!a.fuse_lut) return;
     __threadfence();
     __syncthreads();
@@ -460,11 +465,15 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
     double *dst = reinterpret_cast<double *>(a.dst.data) + pair * a.dst.image_stride;
     constexpr int G = SIO::G;
     const int bins = a.bins;
+    const int E = CT_IDT_EDGE_STRIDE(bins);
     const int ngroups = (int)(a.src.npix / G);
     const int stride = (int)gridDim.x * kThreads;
-    double r[9], lo[3], inv[3];
+    double r[9], rn[9], lo[3], inv[3];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) r[i] = sh.rot[i];
+    for (int i = 0; i < 9; ++i) {
+        r[i] = sh.rot[i];
+        rn[i] = NEXT ? sh.rot[9 + i] : 0.0;
+    }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         lo[j] = sh.grid[j].lo;
@@ -475,11 +484,14 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             const double p = dot3(r + 3 * j, x);
-            const double *edges = tab + j * 4 * (bins + 1), *ent = edges + (bins + 1);
+            const double *edges = tab + j * E;
+            const double2 *ent = reinterpret_cast<const double2 *>(tab + (3 + 2 * j) * E);
             const int ke = bin_estimate(p, lo[j], inv[j], bins);
             // bin index BEFORE folding p == hi into the last bin: ke - (p < edges[ke]) in [0, bins]
             const int k = (int)min((unsigned)(ke - (p < edges[ke] ? 1 : 0)), (unsigned)bins);
-            const double xp = ent[3 * k], fp = ent[3 * k + 1], sl = ent[3 * k + 2];
+            const double xp = edges[k];
+            const double2 fs = ent[k];
+            const double fp = fs.x, sl = fs.y;
             double m = add_rn(mul_rn(sl, sub_rn(p, xp)), fp);   // np.interp: slope*(x - xp[j]) + fp[j]
             if (ROUND32) m = (double)(float)m;                  // float32 d_r buffer, iterative.py:36
             d[j] = sub_rn(m, p);
@@ -488,7 +500,7 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
 #pragma unroll
         for (int c = 0; c < 3; ++c)
             y[c] = add_rn(fma(r[6 + c], d[2], fma(r[3 + c], d[1], mul_rn(r[c], d[0]))), x[c]);
-        if (NEXT) track_range(sh.rot + 9, y, mn, bad);
+        if (NEXT) track_range<false>(rn, y, mn, bad);
     };
     int g = (int)blockIdx.x * kThreads + threadIdx.x;
     typename SIO::Raw raw{};
@@ -541,7 +553,7 @@ __device__ __forceinline__ void remap_dispatch(const RemapArgs &a, int64_t pair,
 
 template <typename SIO, bool VEC>
 __global__ void __launch_bounds__(kThreads, 2) remap_kernel(RemapArgs a) {
-    extern __shared__ double sm_tab[];  // edges + {xp, fp, slope} entries of the three axes
+    extern __shared__ __align__(16) double sm_tab[];  // edges + {fp, slope} entries of the three axes
     __shared__ RemapShared sh;
     const int64_t pair = blockIdx.y;
     const int bins = a.bins;
@@ -550,10 +562,10 @@ __global__ void __launch_bounds__(kThreads, 2) remap_kernel(RemapArgs a) {
     if (threadIdx.x < 9) sh.rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
     else if (threadIdx.x < 18 && next) sh.rot[threadIdx.x] = a.rot_next[pair * a.rot_stride + threadIdx.x - 9];
     if (threadIdx.x >= 32 && threadIdx.x < 35) {
-        const double *tail = lut + 12 * (bins + 1) + 4 * (threadIdx.x - 32);
+        const double *tail = lut + 9 * CT_IDT_EDGE_STRIDE(bins) + 4 * (threadIdx.x - 32);
         sh.grid[threadIdx.x - 32] = AxisGrid{tail[0], tail[1], tail[2], tail[3]};
     }
-    for (int i = threadIdx.x; i < 12 * (bins + 1); i += kThreads) sm_tab[i] = lut[i];
+    for (int i = threadIdx.x; i < 9 * CT_IDT_EDGE_STRIDE(bins); i += kThreads) sm_tab[i] = lut[i];
     __syncthreads();
 
     double mn[6];
@@ -561,10 +573,7 @@ __global__ void __launch_bounds__(kThreads, 2) remap_kernel(RemapArgs a) {
     for (int i = 0; i < 6; ++i) mn[i] = INFINITY;
     bool bad = false;
     remap_dispatch<SIO, VEC>(a, pair, sh, sm_tab, next, mn, bad);
-    if (next) {
-        fold_range(mn, a.keys_next + pair * a.keys_stride, sh.red);
-        if (a.status && __syncthreads_or(bad) && threadIdx.x == 0) a.status[pair] = CT_E_NONFINITE;
-    }
+    if (next) fold_range(mn, a.keys_next + pair * a.keys_stride, sh.red);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -712,14 +721,14 @@ int launch_remap(ct_context *h, const ct_idt_stage *s, const ct_batch *dst, int 
     a.bins = s->bins;
     a.round_f32 = round_f32;
     const int nblk = stream_blocks(h, s->target->npix, s->target->count, 6);
-    const size_t smem = (size_t)12 * (s->bins + 1) * sizeof(double);
+    const size_t smem = (size_t)9 * CT_IDT_EDGE_STRIDE(s->bins) * sizeof(double);
     const dim3 grid(nblk, s->target->count);
     switch (a.kind * 2 + a.vec) {
 #define CT_CASE(ID, T, L, V)                                                                                   \
     case ID:                                                                                                   \
         if (smem > 40 * 1024 && !h->remap_smem_raised[ID]) {                                                   \
             CT_CUDA(h, cudaFuncSetAttribute(remap_kernel<PixelIO<T, L>, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            12 * (CT_IDT_MAX_BINS + 1) * (int)sizeof(double)));                \
+                                            9 * CT_IDT_EDGE_STRIDE(CT_IDT_MAX_BINS) * (int)sizeof(double)));                \
             h->remap_smem_raised[ID] = true;                                                                   \
         }                                                                                                      \
         remap_kernel<PixelIO<T, L>, V><<<grid, kThreads, smem, h->stream>>>(a);                                \

@@ -113,9 +113,10 @@ int ct_linear_transfer_host(ct_handle h, int method, const ct_batch *target,
 /* ------------------------------------------------------------------ IDT (iterative.py:8-59) */
 #define CT_IDT_MAX_BINS 1024
 #define CT_IDT_KEYS 6 /* per pair and iteration: monotone int64 keys of lo[3], -hi[3] */
-/* doubles per pair in a LUT block: per axis edges[bins+1] and {xp,fp,slope}[bins+1], then
+/* doubles per pair in a LUT block: edges[3][E], then {fp,slope}[E] per axis (E = CT_IDT_EDGE_STRIDE), then
  * lo,hi,step,inv per axis (layout documented at K6 in csrc/ct_idt.cu) */
-#define CT_IDT_LUT_DOUBLES(bins) (3 * (4 * ((int64_t)(bins) + 1) + 4))
+#define CT_IDT_EDGE_STRIDE(bins) (((int)(bins) + 2) / 2 * 2) /* bins + 1 rounded up to even */
+#define CT_IDT_LUT_DOUBLES(bins) (3 * (3 * (int64_t)CT_IDT_EDGE_STRIDE(bins) + 4))
 
 typedef struct ct_idt_stage {
     const ct_batch *target;    /* current target state (the input images on iteration 0)   */
