@@ -388,6 +388,9 @@ int ct_linear_transfer_host(ct_handle h, int method, const ct_batch *target, con
 }
 
 // ------------------------------------------------------------------ IDT
+int64_t ct_idt_key_of(double value) { return key_of(value); }
+double ct_idt_value_of(int64_t key) { return value_of(key); }
+
 int ct_idt_keys_init(ct_handle h, int64_t *keys, int64_t n) {
     CT_ENTER(h);
     return launch_keys_init(h, keys, n);

@@ -9,6 +9,9 @@
 // table use un-contracted IEEE ops in np.interp's order.
 #include "ct_context.h"
 
+#ifndef CT_MINB
+#define CT_MINB 2
+#endif
 namespace ct {
 
 // ---------------------------------------------------------------------------------------------
@@ -361,7 +364,7 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Hi
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) hist_kernel(HistArgs a) {
+__global__ void __launch_bounds__(kThreads, CT_MINB) hist_kernel(HistArgs a) {
     extern __shared__ double sm_dyn[];  // edges[3][bins+1], histograms; later reused by the LUT build
     __shared__ HistShared sh;
     const int64_t pair = blockIdx.y;
@@ -552,7 +555,7 @@ __device__ __forceinline__ void remap_dispatch(const RemapArgs &a, int64_t pair,
 }
 
 template <typename SIO, bool VEC>
-__global__ void __launch_bounds__(kThreads, 2) remap_kernel(RemapArgs a) {
+__global__ void __launch_bounds__(kThreads, CT_MINB) remap_kernel(RemapArgs a) {
     extern __shared__ __align__(16) double sm_tab[];  // edges + {fp, slope} entries of the three axes
     __shared__ RemapShared sh;
     const int64_t pair = blockIdx.y;

@@ -148,40 +148,39 @@ class IdtStages:
         s.bins = self.bins
         return s
 
-    def run(self, between=None, timer=None, fuse_lut=None):
-        import contextlib
-        h, lib = self.h, self.h.lib
-        if fuse_lut is None:
-            fuse_lut = between is None
-        tm = timer or (lambda name: contextlib.nullcontext())
+    # ---- stage protocol (schedule.run_idt_schedule)
+    def init(self):
+        h = self.h
         self.counts.zero_()
         self.status.zero_()
-        h.check(lib.ct_idt_keys_init(h.h, ctypes.c_void_p(self.keys.data_ptr()), self.keys.numel()))
+        h.check(h.lib.ct_idt_keys_init(h.h, ctypes.c_void_p(self.keys.data_ptr()), self.keys.numel()))
+
+    def ranges(self, which):
+        h = self.h
         ks, rs = (self.n_iter + 1) * _cabi.CT_IDT_KEYS, self.n_iter * 9
-        with tm("ranges_target"):
-            h.check(lib.ct_idt_ranges(h.h, self.tb, ctypes.c_void_p(self.rot.data_ptr()), rs,
-                                      ctypes.c_void_p(self.keys.data_ptr()), ks, ctypes.c_void_p(self.status.data_ptr())))
-        with tm("ranges_reference"):
-            h.check(lib.ct_idt_ranges(h.h, self.rb, ctypes.c_void_p(self.rot.data_ptr()), rs,
-                                      ctypes.c_void_p(self.keys.data_ptr()), ks, ctypes.c_void_p(self.status.data_ptr())))
-        if between:
-            between("keys", self.keys[:, 0])
-        for it in range(self.n_iter):
-            last = it == self.n_iter - 1
-            s = self._stage(it)
-            with tm(f"hist_{it}"):
-                h.check(lib.ct_idt_hist(h.h, ctypes.byref(s), 1 if fuse_lut else 0))
-            if not fuse_lut:
-                if between:
-                    between("counts", self.counts)
-                with tm(f"lut_{it}"):
-                    h.check(lib.ct_idt_lut(h.h, ctypes.byref(s), 0))
-            with tm(f"remap_{it}"):
-                h.check(lib.ct_idt_remap(h.h, ctypes.byref(s), self.ob if last else self.sb,
-                                         1 if (it == 0 and self.t.dtype == torch.float32) else 0))
-            if between and not last:
-                between("keys", self.keys[:, it + 1])
+        h.check(h.lib.ct_idt_ranges(h.h, self.tb if which == "target" else self.rb, ctypes.c_void_p(self.rot.data_ptr()),
+                                    rs, ctypes.c_void_p(self.keys.data_ptr()), ks, ctypes.c_void_p(self.status.data_ptr())))
+
+    def hist(self, it, fuse_lut):
+        s = self._stage(it)
+        self.h.check(self.h.lib.ct_idt_hist(self.h.h, ctypes.byref(s), 1 if fuse_lut else 0))
+
+    def lut(self, it):
+        s = self._stage(it)
+        self.h.check(self.h.lib.ct_idt_lut(self.h.h, ctypes.byref(s), 0))
+
+    def remap(self, it):
+        s = self._stage(it)
+        last = it == self.n_iter - 1
+        self.h.check(self.h.lib.ct_idt_remap(self.h.h, ctypes.byref(s), self.ob if last else self.sb,
+                                             1 if (it == 0 and self.t.dtype == torch.float32) else 0))
+
+    def result(self):
         return self.out
+
+    def run(self, between=None, timer=None, fuse_lut=None):
+        from .schedule import run_idt_schedule
+        return run_idt_schedule(self, between, timer, fuse_lut)
 
     def raise_for_status(self):
         st = self.status.cpu()

@@ -134,6 +134,12 @@ typedef struct ct_idt_stage {
     int32_t reserved;
 } ct_idt_stage;
 
+/* Host helpers (no device needed): the monotone int64 key of a double and its inverse.  Signed
+ * integer order of keys == floating-point order of values, so per-shard ranges combine with an
+ * integer MIN all-reduce.  Slot layout per pair and iteration: keys of lo[0..2], then -hi[0..2]. */
+int64_t ct_idt_key_of(double value);
+double ct_idt_value_of(int64_t key);
+
 /* Set n keys to "+inf" so that atomic minima can be folded in. */
 int ct_idt_keys_init(ct_handle h, int64_t *keys, int64_t n);
 /* K4: fold min(p), min(-p) of the projections p = rot @ x (iterative.py:34-35, 39-40) of every

@@ -1,0 +1,107 @@
+"""GPU tests of the device-resident API, the batched host API, the stage-by-stage C-ABI calls and
+the multi-GPU drivers (the 2-GPU cases skip on a single-GPU box)."""
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, synthetic_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+
+    import color_transfer_b200  # noqa: F401
+    from color_transfer_b200 import _cabi, batch, device, sharded, synth
+    from oracle import reference_numpy as oracle
+    return torch, _cabi, batch, device, sharded, synth, oracle
+
+
+def _stack(n, h, w, dtype, seed=100):
+    pairs = [synthetic_pair(h, w, seed + i, dtype) for i in range(n)]
+    return np.stack([p[0] for p in pairs]), np.stack([p[1] for p in pairs])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_batched_device_and_host_apis(mods, dtype):
+    torch, _cabi, batch, device, sharded, synth, oracle = mods
+    B, H, W = 5, 33, 47                                   # odd sizes: unaligned image strides
+    t, r = _stack(B, H, W, dtype)
+    dt, dr = torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda()
+    t64, r64 = t.astype(np.float64), r.astype(np.float64)
+    for name, code, fn in (("mkl", _cabi.CT_MKL_MK, oracle.monge_kantorovitch_color_transfer),
+                           ("reinhard", _cabi.CT_REINHARD, oracle.color_transfer_between_images)):
+        dev = device.linear_transfer(code, dt, dr).cpu().numpy()
+        host = batch.linear_transfer_frames(name, t, r)
+        assert np.array_equal(dev, host)                  # same kernels either way
+        for i in range(B):
+            assert np.max(np.abs(dev[i] - fn(t64[i], r64[i]))) < 1e-4
+    rot = sharded.predraw_rotations(B, 4, seed=42)
+    dev = device.idt_transfer(dt, dr, torch.from_numpy(rot).cuda()).cpu().numpy()
+    host = batch.idt_frames(t, r, rotations=rot)
+    assert np.array_equal(dev, host)
+    for i in range(B):
+        want = oracle.iterative_distribution_transfer(t[i], r[i], rotations=rot[i])
+        assert np.max(np.abs(dev[i] - want)) < 1e-10
+    # CHW-memory views (the Runner's layout), batched
+    dt_chw = torch.from_numpy(np.ascontiguousarray(t.transpose(0, 3, 1, 2))).cuda().permute(0, 2, 3, 1)
+    dr_chw = torch.from_numpy(np.ascontiguousarray(r.transpose(0, 3, 1, 2))).cuda().permute(0, 2, 3, 1)
+    assert np.array_equal(device.idt_transfer(dt_chw, dr_chw, torch.from_numpy(rot).cuda()).cpu().numpy(), dev)
+
+
+def test_stage_api_unfused_equals_fused(mods):
+    torch, _cabi, batch, device, sharded, synth, oracle = mods
+    t, r = _stack(3, 64, 80, np.float32, seed=200)
+    dt, dr = torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda()
+    rot = torch.from_numpy(sharded.predraw_rotations(3, 4, seed=1)).cuda()
+    fused = device.idt_transfer(dt, dr, rot).cpu().numpy()
+    seen = []
+    st = device.IdtStages(dt, dr, rot)
+    out = st.run(between=lambda name, tensor: seen.append((name, tuple(tensor.shape))), fuse_lut=False).cpu().numpy()
+    st.raise_for_status()
+    assert np.array_equal(out, fused)
+    assert [s[0] for s in seen] == ["keys"] + ["counts", "keys"] * 3 + ["counts"]
+    assert np.array_equal(device.IdtStages(dt, dr, rot).run().cpu().numpy(), fused)   # fused LUT through the stage API
+
+
+def test_synthetic_frames_and_linear_device_parity(mods):
+    torch, _cabi, batch, device, sharded, synth, oracle = mods
+    t, r = synth.frame_pairs_cuda(2, 135, 240, 7, torch.device("cuda", 0))
+    assert t.shape == (2, 135, 240, 3) and t.dtype == torch.float32 and 0.0 <= float(t.min()) and float(t.max()) <= 1.0
+    out = device.linear_transfer(_cabi.CT_REINHARD, t, r).cpu().numpy()
+    for i in range(2):
+        want = oracle.color_transfer_between_images(t[i].cpu().numpy().astype(np.float64), r[i].cpu().numpy().astype(np.float64))
+        assert np.max(np.abs(out[i] - want)) < 1e-4
+    tn, rn = synth.frame_pair(54, 96, 1000, np.float32)
+    assert tn.shape == (54, 96, 3) and tn.dtype == np.float32
+
+
+def test_row_sharded_drivers_world1(mods):
+    """With one rank the sharded drivers must reproduce the unsharded result bit for bit."""
+    torch, _cabi, batch, device, sharded, synth, oracle = mods
+    t, r = synthetic_pair(70, 90, 41, np.float32)
+    dt, dr = torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda()
+    rot = sharded.predraw_rotations(1, 4, seed=3)[0]
+    out = sharded.idt_transfer_sharded(dt, dr, rot).cpu().numpy()
+    assert np.array_equal(out, device.idt_transfer(dt, dr, torch.from_numpy(rot[None]).cuda()).cpu().numpy())
+    for code in (_cabi.CT_MKL_MK, _cabi.CT_REINHARD, _cabi.CT_CCS):
+        a = sharded.linear_transfer_sharded(code, dt, dr).cpu().numpy()
+        b = device.linear_transfer(code, dt, dr).cpu().numpy()
+        assert np.max(np.abs(a - b)) < 1e-12
+
+
+def test_two_gpu_row_sharding_and_frame_parallel(mods):
+    torch = mods[0]
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(ROOT, "tests", "dist_gpu_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "DIST_GPU_CHECK_OK" in res.stdout
