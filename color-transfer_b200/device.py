@@ -119,7 +119,7 @@ class IdtStages:
         self.rot = rotations.reshape(b, n_iter, 9).contiguous()
         self.keys = torch.empty((b, n_iter + 1, _cabi.CT_IDT_KEYS), dtype=torch.int64, device=dev)
         self.counts = torch.zeros((b, 2, 3, bins), dtype=torch.int64, device=dev)
-        self.lut = torch.empty((b, _cabi.lut_doubles(bins)), dtype=torch.float64, device=dev)
+        self.lut_buf = torch.empty((b, _cabi.lut_doubles(bins)), dtype=torch.float64, device=dev)
         self.status = torch.zeros((b,), dtype=torch.int32, device=dev)
         self.plane = (self.npix + 1) // 2 * 2
         self.state = torch.empty((b, 3, self.plane), dtype=torch.float64, device=dev) if n_iter >= 2 else None
@@ -143,7 +143,7 @@ class IdtStages:
         s.keys_next = None if last else self.keys.data_ptr() + (it + 1) * 48
         s.keys_stride = (self.n_iter + 1) * _cabi.CT_IDT_KEYS
         s.counts = self.counts.data_ptr()
-        s.lut = self.lut.data_ptr()
+        s.lut = self.lut_buf.data_ptr()
         s.status = self.status.data_ptr()
         s.bins = self.bins
         return s

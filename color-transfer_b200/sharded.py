@@ -120,10 +120,11 @@ class CudaIdtBackend:
     def __init__(self, target_shard, reference_shard, rotations, bins, n_iter, handle=None):
         from . import device
         rot = torch.as_tensor(np.ascontiguousarray(rotations, dtype=np.float64)).reshape(1, n_iter, 3, 3)
+        self.shape = target_shard.shape
         self.stages = device.IdtStages(target_shard, reference_shard, rot.to(target_shard.device), bins, n_iter, handle)
 
     def run(self, between):
-        return self.stages.run(between=between, fuse_lut=False)
+        return self.stages.run(between=between, fuse_lut=False).view(self.shape)
 
     def finish(self):
         self.stages.raise_for_status()
