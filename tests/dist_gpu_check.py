@@ -31,7 +31,7 @@ def main():
 
     # ---- IDT: sharded vs single GPU (every rank computes the full problem as the check)
     st_full = device.IdtStages(dt, dr, torch.from_numpy(rot[None]).to(dev))
-    full = st_full.run()
+    full = st_full.run()[0]
     backend = sharded.CudaIdtBackend(dt[a:b].contiguous(), dr[ra:rb].contiguous(), rot, 255, 4)
     counts_log = []
 
