@@ -44,6 +44,7 @@ struct PixelIO {
     static constexpr int G = Vec<T>::G;
     using V = typename Vec<T>::type;
     using elem_t = T;
+    static constexpr int kLayout = LAYOUT;
 
     // scalar access to one pixel (tails, unaligned batches)
     __device__ __forceinline__ static void load1(const T *img, int64_t plane, int64_t p,

@@ -32,6 +32,7 @@ struct ct_context {
     void *stage = nullptr;
     size_t stage_bytes = 0;
 
+    bool hist_smem_raised = false;
     bool remap_smem_raised[8] = {false, false, false, false, false, false, false, false};
 
     // host pipeline

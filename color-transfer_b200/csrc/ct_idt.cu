@@ -8,6 +8,7 @@
 // closed) exactly as np.histogram's corrected estimate, counts are integers, CDFs and the
 // table use un-contracted IEEE ops in np.interp's order.
 #include "ct_context.h"
+#include "ct_pipe.cuh"
 
 #ifndef CT_MINB
 #define CT_MINB 2
@@ -115,40 +116,42 @@ struct RangesArgs {
 };
 
 template <typename IO, bool VEC>
-__device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const double *rot,
+__device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const double *rot, Pipe &pipe,
                                              int first_block, int nblocks, double (&mn)[6], bool &bad) {
     using T = typename IO::elem_t;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
     constexpr int G = IO::G;
-    const int ngroups = (int)(im.npix / G);
-    const int stride = nblocks * kThreads;
-    int g = first_block * kThreads + threadIdx.x;
-    typename IO::Raw raw{};
-    if (g < ngroups) raw = IO::template load_raw<VEC>(base, im.plane_stride, g);
-    while (g < ngroups) {
-        const int gn = g + stride;
-        typename IO::Raw nxt{};
-        if (gn < ngroups) nxt = IO::template load_raw<VEC>(base, im.plane_stride, gn);  // in flight during the math
-        double x[G][3];
-        IO::unpack(raw, x);
+    double r[9];
 #pragma unroll
-        for (int i = 0; i < G; ++i) track_range<true>(rot, x[i], mn, bad);
-        raw = nxt;
-        g = gn;
+    for (int i = 0; i < 9; ++i) r[i] = rot[i];
+    int64_t p = (int64_t)first_block * kThreads + threadIdx.x, step = (int64_t)nblocks * kThreads;
+    if (VEC) {
+        const int ntiles = (int)(im.npix / (kThreads * G));
+        pipe_for_each_group<IO>(pipe, base, im.plane_stride, ntiles, first_block, nblocks,
+                                [&](const typename IO::Raw &raw, int64_t) {
+                                    double x[G][3];
+                                    IO::unpack(raw, x);
+#pragma unroll
+                                    for (int i = 0; i < G; ++i) track_range<true>(r, x[i], mn, bad);
+                                });
+        p = (int64_t)ntiles * kThreads * G + threadIdx.x;   // the tail belongs to block 0
+        step = kThreads;
+        if (first_block != 0) return;
     }
-    if (first_block == 0 && threadIdx.x == 0) {
-        for (int64_t p = (int64_t)ngroups * G; p < im.npix; ++p) {
-            double x[3];
-            IO::load1(base, im.plane_stride, p, x);
-            track_range<true>(rot, x, mn, bad);
-        }
+    for (; p < im.npix; p += step) {
+        double x[3];
+        IO::load1(base, im.plane_stride, p, x);
+        track_range<true>(r, x, mn, bad);
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) ranges_kernel(RangesArgs a) {
+__global__ void __launch_bounds__(kThreads, 3) ranges_kernel(RangesArgs a) {
+    extern __shared__ __align__(16) unsigned char sm_pipe[];
     const int64_t pair = blockIdx.y;
     __shared__ double rot[9];
     __shared__ double red[kWarps][6];
+    Pipe pipe(sm_pipe);
+    if (threadIdx.x == 0) pipe.init();
     if (threadIdx.x < 9) rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
     __syncthreads();
     double mn[6];
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 2) ranges_kernel(RangesArgs a) {
     bool bad = false;
     switch (a.kind * 2 + a.vec) {
 #define CT_CASE(ID, T, L, V) \
-    case ID: ranges_image<PixelIO<T, L>, V>(a.img, pair, rot, blockIdx.x, gridDim.x, mn, bad); break;
+    case ID: ranges_image<PixelIO<T, L>, V>(a.img, pair, rot, pipe, blockIdx.x, gridDim.x, mn, bad); break;
         CT_FOR_EACH_SRC(CT_CASE)
 #undef CT_CASE
     }
@@ -311,14 +314,12 @@ struct HistShared {
 
 template <typename IO, bool VEC, bool NEXT, int CL2>  // CL2: log2(copies) when known at compile time, else -1
 __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const HistShared &sh, const double *edges,
-                                           int bins, int copies_log2_rt, unsigned int *hist, int first_block,
-                                           int nblocks, double (&mn)[6], bool &bad) {
+                                           int bins, int copies_log2_rt, unsigned int *hist, Pipe &pipe,
+                                           int first_block, int nblocks, double (&mn)[6], bool &bad) {
     const int copies_log2 = CL2 >= 0 ? CL2 : copies_log2_rt;
     using T = typename IO::elem_t;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
     constexpr int G = IO::G;
-    const int ngroups = (int)(im.npix / G);
-    const int stride = nblocks * kThreads;
     const int copy = threadIdx.x & ((1 << copies_log2) - 1);
     double r[9], rn[9], lo[3], inv[3];
 #pragma unroll
@@ -341,36 +342,37 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Hi
         }
         if (NEXT) track_range<false>(rn, x, mn, bad);
     };
-    int g = first_block * kThreads + threadIdx.x;
-    typename IO::Raw raw{};
-    if (g < ngroups) raw = IO::template load_raw<VEC>(base, im.plane_stride, g);
-    while (g < ngroups) {
-        const int gn = g + stride;
-        typename IO::Raw nxt{};
-        if (gn < ngroups) nxt = IO::template load_raw<VEC>(base, im.plane_stride, gn);  // in flight during the math
-        double x[G][3];
-        IO::unpack(raw, x);
+    int64_t p = (int64_t)first_block * kThreads + threadIdx.x, step = (int64_t)nblocks * kThreads;
+    if (VEC) {
+        const int ntiles = (int)(im.npix / (kThreads * G));
+        pipe_for_each_group<IO>(pipe, base, im.plane_stride, ntiles, first_block, nblocks,
+                                [&](const typename IO::Raw &raw, int64_t) {
+                                    double x[G][3];
+                                    IO::unpack(raw, x);
 #pragma unroll
-        for (int i = 0; i < G; ++i) one(x[i]);
-        raw = nxt;
-        g = gn;
+                                    for (int i = 0; i < G; ++i) one(x[i]);
+                                });
+        p = (int64_t)ntiles * kThreads * G + threadIdx.x;   // the tail belongs to block 0
+        step = kThreads;
+        if (first_block != 0) return;
     }
-    if (first_block == 0 && threadIdx.x == 0) {
-        for (int64_t p = (int64_t)ngroups * G; p < im.npix; ++p) {
-            double x[3];
-            IO::load1(base, im.plane_stride, p, x);
-            one(x);
-        }
+    for (; p < im.npix; p += step) {
+        double x[3];
+        IO::load1(base, im.plane_stride, p, x);
+        one(x);
     }
 }
 
 __global__ void __launch_bounds__(kThreads, CT_MINB) hist_kernel(HistArgs a) {
-    extern __shared__ double sm_dyn[];  // edges[3][bins+1], histograms; later reused by the LUT build
+    // tile pipeline | edges[3][bins+1] | histograms; the front is later reused by the LUT build
+    extern __shared__ __align__(16) double sm_dyn[];
     __shared__ HistShared sh;
     const int64_t pair = blockIdx.y;
     const int bins = a.bins;
-    double *edges = sm_dyn;
-    unsigned int *hist = reinterpret_cast<unsigned int *>(sm_dyn + 3 * (bins + 1));
+    Pipe pipe(sm_dyn);
+    double *edges = sm_dyn + kPipeBytes / 8;
+    unsigned int *hist = reinterpret_cast<unsigned int *>(edges + 3 * (bins + 1));
+    if (threadIdx.x == 0) pipe.init();
     const int z = (int)blockIdx.x < a.nblk[0] ? 0 : 1;
     const int first_block = z == 0 ? blockIdx.x : blockIdx.x - a.nblk[0];
     const bool next = (z == 1) && a.rot_next != nullptr && a.keys_next != nullptr;
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, CT_MINB) hist_kernel(HistArgs a) {
         CT_FOR_EACH_SRC(CT_CASE_##NEXTV##_##CL2V)                                                        \
     }
 #define CT_HIST_CALL(T, L, V, NEXTV, CL2V)                                                               \
-    hist_image<PixelIO<T, L>, V, NEXTV, CL2V>(a.img[z], pair, sh, edges, bins, a.copies_log2, hist, first_block, a.nblk[z], mn, bad)
+    hist_image<PixelIO<T, L>, V, NEXTV, CL2V>(a.img[z], pair, sh, edges, bins, a.copies_log2, hist, pipe, first_block, a.nblk[z], mn, bad)
 #define CT_CASE_true_3(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, true, 3); break;
 #define CT_CASE_false_3(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, false, 3); break;
 #define CT_CASE_true_g(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, true, -1); break;
@@ -462,15 +464,13 @@ struct RemapShared {
 
 template <typename SIO, typename DIO, bool VEC, bool NEXT, bool ROUND32>
 __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, const RemapShared &sh,
-                                            const double *tab, double (&mn)[6], bool &bad) {
+                                            const double *tab, Pipe &pipe, double (&mn)[6], bool &bad) {
     using TS = typename SIO::elem_t;
     const TS *src = reinterpret_cast<const TS *>(a.src.data) + pair * a.src.image_stride;
     double *dst = reinterpret_cast<double *>(a.dst.data) + pair * a.dst.image_stride;
     constexpr int G = SIO::G;
     const int bins = a.bins;
     const int E = CT_IDT_EDGE_STRIDE(bins);
-    const int ngroups = (int)(a.src.npix / G);
-    const int stride = (int)gridDim.x * kThreads;
     double r[9], rn[9], lo[3], inv[3];
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
@@ -505,28 +505,26 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
             y[c] = add_rn(fma(r[6 + c], d[2], fma(r[3 + c], d[1], mul_rn(r[c], d[0]))), x[c]);
         if (NEXT) track_range<false>(rn, y, mn, bad);
     };
-    int g = (int)blockIdx.x * kThreads + threadIdx.x;
-    typename SIO::Raw raw{};
-    if (g < ngroups) raw = SIO::template load_raw<VEC>(src, a.src.plane_stride, g);
-    while (g < ngroups) {
-        const int gn = g + stride;
-        typename SIO::Raw nxt{};
-        if (gn < ngroups) nxt = SIO::template load_raw<VEC>(src, a.src.plane_stride, gn);  // in flight during the math
-        double x[G][3], y[G][3];
-        SIO::unpack(raw, x);
+    int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x, step = (int64_t)gridDim.x * kThreads;
+    if (VEC) {
+        const int ntiles = (int)(a.src.npix / (kThreads * G));
+        pipe_for_each_group<SIO>(pipe, src, a.src.plane_stride, ntiles, blockIdx.x, gridDim.x,
+                                 [&](const typename SIO::Raw &raw, int64_t pix0) {
+                                     double x[G][3], y[G][3];
+                                     SIO::unpack(raw, x);
 #pragma unroll
-        for (int i = 0; i < G; ++i) one(x[i], y[i]);
-        DIO::template store<VEC, G>(dst, a.dst.plane_stride, (int64_t)g * G, y);
-        raw = nxt;
-        g = gn;
+                                     for (int i = 0; i < G; ++i) one(x[i], y[i]);
+                                     DIO::template store<true, G>(dst, a.dst.plane_stride, pix0, y);
+                                 });
+        p = (int64_t)ntiles * kThreads * G + threadIdx.x;   // the tail belongs to block 0
+        step = kThreads;
+        if (blockIdx.x != 0) return;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int64_t p = (int64_t)ngroups * G; p < a.src.npix; ++p) {
-            double x[3], y[3];
-            SIO::load1(src, a.src.plane_stride, p, x);
-            one(x, y);
-            DIO::store1(dst, a.dst.plane_stride, p, y);
-        }
+    for (; p < a.src.npix; p += step) {
+        double x[3], y[3];
+        SIO::load1(src, a.src.plane_stride, p, x);
+        one(x, y);
+        DIO::store1(dst, a.dst.plane_stride, p, y);
     }
 }
 
@@ -534,30 +532,33 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
 // block-uniform runtime switches inside
 template <typename SIO, bool VEC>
 __device__ __forceinline__ void remap_dispatch(const RemapArgs &a, int64_t pair, const RemapShared &sh,
-                                               const double *tab, bool next, double (&mn)[6], bool &bad) {
+                                               const double *tab, Pipe &pipe, bool next, double (&mn)[6], bool &bad) {
     using StateIO = PixelIO<double, CT_CHW>;
     using FinalIO = PixelIO<double, CT_HWC>;
     if (a.round_f32) {  // iteration 0 of float32 input: the state buffer is always the destination or n_iter == 1
         if (a.dst_layout == CT_CHW) {
-            if (next) remap_image<SIO, StateIO, VEC, true, true>(a, pair, sh, tab, mn, bad);
-            else remap_image<SIO, StateIO, VEC, false, true>(a, pair, sh, tab, mn, bad);
+            if (next) remap_image<SIO, StateIO, VEC, true, true>(a, pair, sh, tab, pipe, mn, bad);
+            else remap_image<SIO, StateIO, VEC, false, true>(a, pair, sh, tab, pipe, mn, bad);
         } else {
-            if (next) remap_image<SIO, FinalIO, VEC, true, true>(a, pair, sh, tab, mn, bad);
-            else remap_image<SIO, FinalIO, VEC, false, true>(a, pair, sh, tab, mn, bad);
+            if (next) remap_image<SIO, FinalIO, VEC, true, true>(a, pair, sh, tab, pipe, mn, bad);
+            else remap_image<SIO, FinalIO, VEC, false, true>(a, pair, sh, tab, pipe, mn, bad);
         }
     } else if (a.dst_layout == CT_CHW) {
-        if (next) remap_image<SIO, StateIO, VEC, true, false>(a, pair, sh, tab, mn, bad);
-        else remap_image<SIO, StateIO, VEC, false, false>(a, pair, sh, tab, mn, bad);
+        if (next) remap_image<SIO, StateIO, VEC, true, false>(a, pair, sh, tab, pipe, mn, bad);
+        else remap_image<SIO, StateIO, VEC, false, false>(a, pair, sh, tab, pipe, mn, bad);
     } else {
-        if (next) remap_image<SIO, FinalIO, VEC, true, false>(a, pair, sh, tab, mn, bad);
-        else remap_image<SIO, FinalIO, VEC, false, false>(a, pair, sh, tab, mn, bad);
+        if (next) remap_image<SIO, FinalIO, VEC, true, false>(a, pair, sh, tab, pipe, mn, bad);
+        else remap_image<SIO, FinalIO, VEC, false, false>(a, pair, sh, tab, pipe, mn, bad);
     }
 }
 
 template <typename SIO, bool VEC>
 __global__ void __launch_bounds__(kThreads, CT_MINB) remap_kernel(RemapArgs a) {
-    extern __shared__ __align__(16) double sm_tab[];  // edges + {fp, slope} entries of the three axes
+    extern __shared__ __align__(16) double sm_remap[];  // tile pipeline | edges + {fp, slope} entries of the three axes
     __shared__ RemapShared sh;
+    Pipe pipe(sm_remap);
+    double *sm_tab = sm_remap + kPipeBytes / 8;
+    if (threadIdx.x == 0) pipe.init();
     const int64_t pair = blockIdx.y;
     const int bins = a.bins;
     const bool next = a.rot_next != nullptr && a.keys_next != nullptr;
@@ -575,7 +576,7 @@ __global__ void __launch_bounds__(kThreads, CT_MINB) remap_kernel(RemapArgs a) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) mn[i] = INFINITY;
     bool bad = false;
-    remap_dispatch<SIO, VEC>(a, pair, sh, sm_tab, next, mn, bad);
+    remap_dispatch<SIO, VEC>(a, pair, sh, sm_tab, pipe, next, mn, bad);
     if (next) fold_range(mn, a.keys_next + pair * a.keys_stride, sh.red);
 }
 
@@ -604,7 +605,7 @@ int launch_ranges(ct_context *h, const ct_batch *img, const double *rot, int64_t
     if (!rot || !keys) return fail(h, CT_E_INVALID, "rot/keys is NULL");
     RangesArgs a{img_of(img), src_kind(img), vec_ok(img), rot, rot_stride, keys, keys_stride, status};
     const int nblk = stream_blocks(h, img->npix, img->count, 8);
-    ranges_kernel<<<dim3(nblk, img->count), kThreads, 0, h->stream>>>(a);
+    ranges_kernel<<<dim3(nblk, img->count), kThreads, kPipeBytes, h->stream>>>(a);
     h->launches++;
     CT_CUDA(h, cudaGetLastError());
     return CT_OK;
@@ -681,8 +682,12 @@ int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt
     CT_TRY(ensure_scratch(h, B));
     a.tickets = h->tickets;
     a.lut = lut_args(s, 0, trace, trace_iter, trace_niter);
-    const size_t smem = (size_t)3 * (s->bins + 1) * sizeof(double) +
+    const size_t smem = (size_t)kPipeBytes + (size_t)3 * (s->bins + 1) * sizeof(double) +
                         (size_t)((3 * s->bins) << a.copies_log2) * sizeof(unsigned int);  // >= 3*bins doubles for the LUT build
+    if (smem > 48 * 1024 && !h->hist_smem_raised) {
+        CT_CUDA(h, cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        h->hist_smem_raised = true;
+    }
     hist_kernel<<<dim3(a.nblk[0] + a.nblk[1], B), kThreads, smem, h->stream>>>(a);
     h->launches++;
     CT_CUDA(h, cudaGetLastError());
@@ -724,14 +729,14 @@ int launch_remap(ct_context *h, const ct_idt_stage *s, const ct_batch *dst, int 
     a.bins = s->bins;
     a.round_f32 = round_f32;
     const int nblk = stream_blocks(h, s->target->npix, s->target->count, 6);
-    const size_t smem = (size_t)9 * CT_IDT_EDGE_STRIDE(s->bins) * sizeof(double);
+    const size_t smem = (size_t)kPipeBytes + (size_t)9 * CT_IDT_EDGE_STRIDE(s->bins) * sizeof(double);
     const dim3 grid(nblk, s->target->count);
     switch (a.kind * 2 + a.vec) {
 #define CT_CASE(ID, T, L, V)                                                                                   \
     case ID:                                                                                                   \
         if (smem > 40 * 1024 && !h->remap_smem_raised[ID]) {                                                   \
             CT_CUDA(h, cudaFuncSetAttribute(remap_kernel<PixelIO<T, L>, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            9 * CT_IDT_EDGE_STRIDE(CT_IDT_MAX_BINS) * (int)sizeof(double)));                \
+                                            kPipeBytes + 9 * CT_IDT_EDGE_STRIDE(CT_IDT_MAX_BINS) * (int)sizeof(double)));                \
             h->remap_smem_raised[ID] = true;                                                                   \
         }                                                                                                      \
         remap_kernel<PixelIO<T, L>, V><<<grid, kThreads, smem, h->stream>>>(a);                                \

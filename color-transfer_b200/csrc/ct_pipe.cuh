@@ -1,0 +1,124 @@
+// Streaming tile pipeline: TMA bulk copies (cp.async.bulk, SASS UBLKCP) fill a ring of
+// shared-memory stages, mbarriers (complete_tx) signal arrival, consumers hand a stage back
+// through a second mbarrier.  The bytes in flight live in shared memory instead of registers:
+// kStages x 12 KB per CTA are outstanding while every thread computes on 12 registers of raw
+// pixels, which is what lets these fp64-heavy kernels hide HBM latency at 2-3 CTAs per SM.
+//
+// A tile is kThreads pixel groups (1024 f32 pixels or 512 f64 pixels = 12 KB).  Interleaved
+// images need one bulk copy per tile, planar images three (one per channel plane).  Thread i then
+// reads its group with conflict-free 128-bit LDS (stride 48 B -> the 16 B bank groups 3i mod 8 of
+// a quarter warp are distinct; planar: stride 16 B).
+#pragma once
+
+#include "ct_common.cuh"
+
+namespace ct {
+
+constexpr int kStages = 3;
+constexpr int kTileBytes = kThreads * 48;  // 12 KB for every (dtype, layout)
+constexpr int kPipeBytes = kStages * kTileBytes + 2 * kStages * 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Shared-memory view of one CTA's pipeline (carved from dynamic shared memory, 16 B aligned).
+struct Pipe {
+    unsigned char *stage;  // kStages * kTileBytes
+    uint64_t *full;        // [kStages]
+    uint64_t *empty;       // [kStages]
+    __device__ __forceinline__ explicit Pipe(void *base)
+        : stage(static_cast<unsigned char *>(base)),
+          full(reinterpret_cast<uint64_t *>(static_cast<unsigned char *>(base) + kStages * kTileBytes)),
+          empty(full + kStages) {}
+    // one thread; followed by __syncthreads() in the caller
+    __device__ __forceinline__ void init() {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+};
+
+// Runs f(raw, first_pixel_of_group) on every pixel group of the FULL tiles first_tile, first_tile + tile_stride, ...
+// of one image; every thread of the CTA must call it (block-uniform trip count).  `pipe` must be
+// freshly initialised (phase 0) for each call.
+template <typename IO, typename F>
+__device__ __forceinline__ void pipe_for_each_group(Pipe &pipe, const typename IO::elem_t *img, int64_t plane,
+                                                    int ntiles, int first_tile, int tile_stride, F &&f) {
+    using T = typename IO::elem_t;
+    constexpr int G = IO::G;
+    constexpr int kTilePx = kThreads * G;
+    const int mine = first_tile < ntiles ? (ntiles - first_tile + tile_stride - 1) / tile_stride : 0;
+    auto issue = [&](int i) {  // thread 0 only
+        const int s = i % kStages;
+        const int64_t p0 = (int64_t)(first_tile + (int64_t)i * tile_stride) * kTilePx;
+        unsigned char *dst = pipe.stage + s * kTileBytes;
+        mbar_expect_tx(&pipe.full[s], kTileBytes);
+        if (IO::kLayout == CT_HWC) {
+            bulk_g2s(dst, img + 3 * p0, kTileBytes, &pipe.full[s]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) bulk_g2s(dst + c * (kTileBytes / 3), img + c * plane + p0, kTileBytes / 3, &pipe.full[s]);
+        }
+    };
+    if (threadIdx.x == 0)
+        for (int i = 0; i < kStages && i < mine; ++i) issue(i);
+    for (int i = 0; i < mine; ++i) {
+        const int s = i % kStages;
+        const uint32_t parity = (i / kStages) & 1;
+        mbar_wait(&pipe.full[s], parity);
+        typename IO::Raw raw;
+        {
+            using V = typename IO::V;
+            const unsigned char *src = pipe.stage + s * kTileBytes;
+            if (IO::kLayout == CT_HWC) {
+                const V *v = reinterpret_cast<const V *>(src) + 3 * threadIdx.x;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) *reinterpret_cast<V *>(&raw.e[k * G]) = v[k];
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    *reinterpret_cast<V *>(&raw.e[c * G]) = reinterpret_cast<const V *>(src + c * (kTileBytes / 3))[threadIdx.x];
+            }
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&pipe.empty[s]);  // this warp has copied its groups out
+        if (threadIdx.x == 0 && i + kStages < mine) {
+            mbar_wait(&pipe.empty[s], parity);  // all 8 warps are done with the stage
+            issue(i + kStages);
+        }
+        f(raw, (int64_t)(first_tile + (int64_t)i * tile_stride) * kTilePx + (int64_t)threadIdx.x * G);
+    }
+    (void)sizeof(T);
+}
+
+}  // namespace ct
