@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libct_b200.so")
+LIB_PATH = os.environ.get("CT_B200_LIB") or os.path.join(_HERE, "libct_b200.so")  # override: A/B builds only
 
 CT_OK, CT_E_INVALID, CT_E_CUDA, CT_E_NONFINITE, CT_E_NOT_PD, CT_E_SINGULAR, CT_E_UNSUPPORTED, CT_E_NOMEM = (
     0, -1, -2, -3, -4, -5, -6, -7)
@@ -67,7 +67,7 @@ SIGNATURES = {
     "ct_idt_key_of": (ctypes.c_int64, [ctypes.c_double]),
     "ct_idt_value_of": (ctypes.c_double, [ctypes.c_int64]),
     "ct_idt_keys_init": (ctypes.c_int, [_P, _P, ctypes.c_int64]),
-    "ct_idt_ranges": (ctypes.c_int, [_P, _BP, _P, ctypes.c_int64, _P, ctypes.c_int64, _P]),
+    "ct_idt_ranges": (ctypes.c_int, [_P, _BP, _P, ctypes.c_int64, ctypes.c_int32, _P, ctypes.c_int64, _P]),
     "ct_idt_hist": (ctypes.c_int, [_P, ctypes.POINTER(IdtStage), ctypes.c_int]),
     "ct_idt_lut": (ctypes.c_int, [_P, ctypes.POINTER(IdtStage), ctypes.c_int]),
     "ct_idt_remap": (ctypes.c_int, [_P, ctypes.POINTER(IdtStage), _BP, ctypes.c_int]),

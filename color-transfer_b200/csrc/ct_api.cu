@@ -145,8 +145,10 @@ static int idt_run(ct_context *h, const ct_batch *target, const ct_batch *refere
     CT_CUDA(h, cudaMemsetAsync(st, 0, sizeof(int32_t) * (size_t)B, h->stream));
     const int64_t keys_stride = (int64_t)(n_iter + 1) * CT_IDT_KEYS, rot_stride = (int64_t)n_iter * 9;
     CT_TRY(launch_keys_init(h, L.keys, (int64_t)B * keys_stride));
-    CT_TRY(launch_ranges(h, target, rotations, rot_stride, L.keys, keys_stride, st));
-    CT_TRY(launch_ranges(h, reference, rotations, rot_stride, L.keys, keys_stride, st));
+    // iteration 0 needs the target's range; the reference never changes, so its range under
+    // EVERY rotation is taken in the same single pass over it
+    CT_TRY(launch_ranges(h, target, rotations, rot_stride, 1, L.keys, keys_stride, st));
+    CT_TRY(launch_ranges(h, reference, rotations, rot_stride, n_iter, L.keys, keys_stride, st));
 
     ct_batch state{};
     state.data = L.state;
@@ -395,10 +397,10 @@ int ct_idt_keys_init(ct_handle h, int64_t *keys, int64_t n) {
     CT_ENTER(h);
     return launch_keys_init(h, keys, n);
 }
-int ct_idt_ranges(ct_handle h, const ct_batch *images, const double *rot, int64_t rot_stride, int64_t *keys,
-                  int64_t keys_stride, int32_t *status) {
+int ct_idt_ranges(ct_handle h, const ct_batch *images, const double *rot, int64_t rot_stride, int32_t n_rot,
+                  int64_t *keys, int64_t keys_stride, int32_t *status) {
     CT_ENTER(h);
-    return launch_ranges(h, images, rot, rot_stride, keys, keys_stride, status);
+    return launch_ranges(h, images, rot, rot_stride, n_rot, keys, keys_stride, status);
 }
 int ct_idt_hist(ct_handle h, const ct_idt_stage *s, int fuse_lut) {
     CT_ENTER(h);

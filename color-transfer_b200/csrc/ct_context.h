@@ -104,7 +104,7 @@ int launch_apply(ct_context *h, int method, const ct_batch *target, const double
 
 // ct_idt.cu
 int launch_keys_init(ct_context *h, int64_t *keys, int64_t n);
-int launch_ranges(ct_context *h, const ct_batch *img, const double *rot, int64_t rot_stride,
+int launch_ranges(ct_context *h, const ct_batch *img, const double *rot, int64_t rot_stride, int n_rot,
                   int64_t *keys, int64_t keys_stride, int32_t *status);
 int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt_trace *trace,
                 int trace_iter, int trace_niter);

@@ -58,6 +58,15 @@ __device__ __forceinline__ int bin_from(int kest, double p, double e, int bins) 
     const int k = kest - (p < e ? 1 : 0);
     return (int)min((unsigned)k, (unsigned)(bins - 1));
 }
+// The same decision with edges[k'] recomputed as np.linspace does (k'*step + lo, separate IEEE
+// multiply and add; k' as a double falls out of the magic-number trick for free).  k' = bins is
+// not special-cased to `hi`: either outcome of the comparison folds into the last bin.
+__device__ __forceinline__ int bin_exact(double p, double lo, double inv, double step, int bins) {
+    const double u = fma(p - lo, inv, kMagic);
+    const double e = add_rn(mul_rn(u - kMagic, step), lo);
+    const int k = __double2loint(u) - (p < e ? 1 : 0);
+    return (int)min((unsigned)k, (unsigned)(bins - 1));
+}
 
 __device__ __forceinline__ bool not_finite(double p) {
     return (__double2hiint(p) & 0x7ff00000) == 0x7ff00000;
@@ -105,9 +114,12 @@ __global__ void keys_init_kernel(int64_t *keys, int64_t n) {
 // ---------------------------------------------------------------------------------------------
 // K4: projected range of one image under one rotation (iterative.py:34-35, 39-40)
 // ---------------------------------------------------------------------------------------------
+constexpr int kMaxRot = 4;  // rotations evaluated per pass over an image
+
 struct RangesArgs {
     Img img;
     int kind, vec;
+    int n_rot;  // 1..kMaxRot consecutive rotations (rot + 9k) folded into consecutive key slots (keys + 6k)
     const double *rot;
     int64_t rot_stride;
     int64_t *keys;
@@ -116,14 +128,27 @@ struct RangesArgs {
 };
 
 template <typename IO, bool VEC>
-__device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const double *rot, Pipe &pipe,
-                                             int first_block, int nblocks, double (&mn)[6], bool &bad) {
+__device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const double *rot, int n_rot, Pipe &pipe,
+                                             int first_block, int nblocks, double (&mn)[kMaxRot][6], bool &bad) {
     using T = typename IO::elem_t;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
     constexpr int G = IO::G;
-    double r[9];
+    auto group = [&](const double(*x)[3], int n) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) r[i] = rot[i];
+        for (int k = 0; k < kMaxRot; ++k) {
+            if (k < n_rot) {
+                double r[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) r[i] = rot[9 * k + i];   // shared-memory broadcast
+#pragma unroll
+                for (int i = 0; i < G; ++i)
+                    if (i < n) {
+                        if (k == 0) track_range<true>(r, x[i], mn[k], bad);
+                        else track_range<false>(r, x[i], mn[k], bad);
+                    }
+            }
+        }
+    };
     int64_t p = (int64_t)first_block * kThreads + threadIdx.x, step = (int64_t)nblocks * kThreads;
     if (VEC) {
         const int ntiles = (int)(im.npix / (kThreads * G));
@@ -131,40 +156,47 @@ __device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const 
                                 [&](const typename IO::Raw &raw, int64_t) {
                                     double x[G][3];
                                     IO::unpack(raw, x);
-#pragma unroll
-                                    for (int i = 0; i < G; ++i) track_range<true>(r, x[i], mn, bad);
+                                    group(x, G);
                                 });
         p = (int64_t)ntiles * kThreads * G + threadIdx.x;   // the tail belongs to block 0
         step = kThreads;
         if (first_block != 0) return;
     }
     for (; p < im.npix; p += step) {
-        double x[3];
-        IO::load1(base, im.plane_stride, p, x);
-        track_range<true>(r, x, mn, bad);
+        double x[G][3];
+        IO::load1(base, im.plane_stride, p, x[0]);
+        group(x, 1);
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) ranges_kernel(RangesArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) ranges_kernel(RangesArgs a) {
     extern __shared__ __align__(16) unsigned char sm_pipe[];
     const int64_t pair = blockIdx.y;
-    __shared__ double rot[9];
+    __shared__ double rot[9 * kMaxRot];
     __shared__ double red[kWarps][6];
     Pipe pipe(sm_pipe);
     if (threadIdx.x == 0) pipe.init();
-    if (threadIdx.x < 9) rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
+    if (threadIdx.x < 9 * a.n_rot) rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
     __syncthreads();
-    double mn[6];
+    double mn[kMaxRot][6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) mn[i] = INFINITY;
+    for (int k = 0; k < kMaxRot; ++k)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) mn[k][i] = INFINITY;
     bool bad = false;
     switch (a.kind * 2 + a.vec) {
 #define CT_CASE(ID, T, L, V) \
-    case ID: ranges_image<PixelIO<T, L>, V>(a.img, pair, rot, pipe, blockIdx.x, gridDim.x, mn, bad); break;
+    case ID: ranges_image<PixelIO<T, L>, V>(a.img, pair, rot, a.n_rot, pipe, blockIdx.x, gridDim.x, mn, bad); break;
         CT_FOR_EACH_SRC(CT_CASE)
 #undef CT_CASE
     }
-    fold_range(mn, a.keys + pair * a.keys_stride, red);
+#pragma unroll
+    for (int k = 0; k < kMaxRot; ++k) {
+        if (k < a.n_rot) {
+            fold_range(mn[k], a.keys + pair * a.keys_stride + CT_IDT_KEYS * k, red);
+            __syncthreads();
+        }
+    }
     if (a.status && __syncthreads_or(bad) && threadIdx.x == 0) a.status[pair] = CT_E_NONFINITE;
 }
 
@@ -283,7 +315,8 @@ __global__ void __launch_bounds__(kThreads) lut_kernel(LutArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 // K5: projection + shared-memory-privatised histograms (iterative.py:34-35, 42-43)
-// Each block serves one image of one pair.  The block's three 1-D histograms are replicated
+// Each block serves one image of one pair.  Nothing but the projection rows, the grid and the
+// pipeline state lives in registers (72), so 3 CTAs = 24 warps fit per SM.  The block's three 1-D histograms are replicated
 // R times, copy = lane % R, copies interleaved (index = bin*R + copy) so that the lanes of a
 // warp that hit the same or neighbouring bins (smooth images) land in different banks.
 // The exact edges of the three axes sit in shared memory next to them.
@@ -306,41 +339,36 @@ struct HistArgs {
 };
 
 struct HistShared {
-    double rot[18];
+    double rot[9];
     AxisGrid grid[3];
-    double red[kWarps][6];
     bool is_last;
 };
 
-template <typename IO, bool VEC, bool NEXT, int CL2>  // CL2: log2(copies) when known at compile time, else -1
-__device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const HistShared &sh, const double *edges,
+template <typename IO, bool VEC, int CL2>  // CL2: log2(copies) when known at compile time, else -1
+__device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const HistShared &sh,
                                            int bins, int copies_log2_rt, unsigned int *hist, Pipe &pipe,
-                                           int first_block, int nblocks, double (&mn)[6], bool &bad) {
+                                           int first_block, int nblocks) {
     const int copies_log2 = CL2 >= 0 ? CL2 : copies_log2_rt;
     using T = typename IO::elem_t;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
     constexpr int G = IO::G;
     const int copy = threadIdx.x & ((1 << copies_log2) - 1);
-    double r[9], rn[9], lo[3], inv[3];
+    double r[9], lo[3], inv[3], stp[3];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        r[i] = sh.rot[i];
-        rn[i] = NEXT ? sh.rot[9 + i] : 0.0;
-    }
+    for (int i = 0; i < 9; ++i) r[i] = sh.rot[i];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         lo[j] = sh.grid[j].lo;
         inv[j] = sh.grid[j].inv;
+        stp[j] = sh.grid[j].step;
     }
     auto one = [&](const double(&x)[3]) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             const double p = dot3(r + 3 * j, x);
-            const int ke = bin_estimate(p, lo[j], inv[j], bins);
-            const int k = bin_from(ke, p, (edges + j * (bins + 1))[ke], bins);
+            const int k = bin_exact(p, lo[j], inv[j], stp[j], bins);
             atomicAdd(&(hist + ((j * bins) << copies_log2) + copy)[k << copies_log2], 1u);
         }
-        if (NEXT) track_range<false>(rn, x, mn, bad);
     };
     int64_t p = (int64_t)first_block * kThreads + threadIdx.x, step = (int64_t)nblocks * kThreads;
     if (VEC) {
@@ -363,22 +391,19 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Hi
     }
 }
 
-__global__ void __launch_bounds__(kThreads, CT_MINB) hist_kernel(HistArgs a) {
-    // tile pipeline | edges[3][bins+1] | histograms; the front is later reused by the LUT build
+__global__ void __launch_bounds__(kThreads, 3) hist_kernel(HistArgs a) {
+    // tile pipeline | histograms; the front is later reused by the LUT build
     extern __shared__ __align__(16) double sm_dyn[];
     __shared__ HistShared sh;
     const int64_t pair = blockIdx.y;
     const int bins = a.bins;
     Pipe pipe(sm_dyn);
-    double *edges = sm_dyn + kPipeBytes / 8;
-    unsigned int *hist = reinterpret_cast<unsigned int *>(edges + 3 * (bins + 1));
+    unsigned int *hist = reinterpret_cast<unsigned int *>(sm_dyn + kPipeBytes / 8);
     if (threadIdx.x == 0) pipe.init();
     const int z = (int)blockIdx.x < a.nblk[0] ? 0 : 1;
     const int first_block = z == 0 ? blockIdx.x : blockIdx.x - a.nblk[0];
-    const bool next = (z == 1) && a.rot_next != nullptr && a.keys_next != nullptr;
 
     if (threadIdx.x < 9) sh.rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
-    else if (threadIdx.x < 18 && next) sh.rot[threadIdx.x] = a.rot_next[pair * a.rot_stride + threadIdx.x - 9];
     if (threadIdx.x >= 32 && threadIdx.x < 35) {
         bool finite;
         sh.grid[threadIdx.x - 32] = grid_from_keys(a.keys + pair * a.keys_stride, threadIdx.x - 32, bins, finite);
@@ -386,34 +411,20 @@ __global__ void __launch_bounds__(kThreads, CT_MINB) hist_kernel(HistArgs a) {
     const int nslots = (3 * bins) << a.copies_log2;
     for (int i = threadIdx.x; i < nslots; i += kThreads) hist[i] = 0u;
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 * (bins + 1); i += kThreads) {
-        const int j = i / (bins + 1);
-        edges[i] = edge(sh.grid[j], i - j * (bins + 1), bins);
-    }
-    __syncthreads();
 
-    double mn[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) mn[i] = INFINITY;
-    bool bad = false;
     const int sel = a.kind[z] * 2 + a.vec[z];
-#define CT_HIST_SWITCH(NEXTV, CL2V)                                                                          \
-    switch (sel) {                                                                                       \
-        CT_FOR_EACH_SRC(CT_CASE_##NEXTV##_##CL2V)                                                        \
-    }
-#define CT_HIST_CALL(T, L, V, NEXTV, CL2V)                                                               \
-    hist_image<PixelIO<T, L>, V, NEXTV, CL2V>(a.img[z], pair, sh, edges, bins, a.copies_log2, hist, pipe, first_block, a.nblk[z], mn, bad)
-#define CT_CASE_true_3(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, true, 3); break;
-#define CT_CASE_false_3(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, false, 3); break;
-#define CT_CASE_true_g(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, true, -1); break;
-#define CT_CASE_false_g(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, false, -1); break;
+#define CT_HIST_CALL(T, L, V, CL2V) \
+    hist_image<PixelIO<T, L>, V, CL2V>(a.img[z], pair, sh, bins, a.copies_log2, hist, pipe, first_block, a.nblk[z])
+#define CT_CASE_3(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, 3); break;
+#define CT_CASE_g(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, -1); break;
     if (a.copies_log2 == 3) {  // bins <= 256: the default 255
-        if (next) { CT_HIST_SWITCH(true, 3) } else { CT_HIST_SWITCH(false, 3) }
+        switch (sel) { CT_FOR_EACH_SRC(CT_CASE_3) }
     } else {
-        if (next) { CT_HIST_SWITCH(true, g) } else { CT_HIST_SWITCH(false, g) }
+        switch (sel) { CT_FOR_EACH_SRC(CT_CASE_g) }
     }
-#undef CT_HIST_SWITCH
 #undef CT_HIST_CALL
+#undef CT_CASE_3
+#undef CT_CASE_g
     __syncthreads();
     // flush: sum the copies of each bin, one 64-bit integer atomic per non-empty bin
     uint64_t *cnt = a.counts + (pair * 2 + z) * 3 * (int64_t)bins;
@@ -423,7 +434,6 @@ __global__ void __launch_bounds__(kThreads, CT_MINB) hist_kernel(HistArgs a) {
         for (int c = 0; c < copies; ++c) s += hist[(i << a.copies_log2) + c];
         if (s) atomicAdd(reinterpret_cast<unsigned long long *>(cnt + i), (unsigned long long)s);
     }
-    if (next) fold_range(mn, a.keys_next + pair * a.keys_stride, sh.red);
     if (!a.fuse_lut) return;
     __threadfence();
     __syncthreads();
@@ -583,6 +593,19 @@ __global__ void __launch_bounds__(kThreads, CT_MINB) remap_kernel(RemapArgs a) {
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
+// blocks per image for a persistent, tile-strided launch: one wave of `occ` resident CTAs per SM
+// shared by `units` images, never more than one CTA per tile
+template <typename K>
+static int resident_blocks(const ct_context *h, K kernel, size_t smem, int64_t npix, int64_t units) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+    const int64_t want = (npix / 2 + kThreads - 1) / kThreads;
+    int64_t cap = ((int64_t)h->sm_count * occ) / (units > 0 ? units : 1);
+    if (cap < 1) cap = 1;
+    const int64_t n = want < cap ? want : cap;
+    return (int)(n < 1 ? 1 : n);
+}
+
 static int stream_blocks(const ct_context *h, int64_t npix, int64_t units, int per_sm) {
     const int64_t want = (npix / 2 + kThreads - 1) / kThreads;
     int64_t cap = ((int64_t)h->sm_count * per_sm) / (units > 0 ? units : 1);
@@ -599,15 +622,19 @@ int launch_keys_init(ct_context *h, int64_t *keys, int64_t n) {
     return CT_OK;
 }
 
-int launch_ranges(ct_context *h, const ct_batch *img, const double *rot, int64_t rot_stride,
+int launch_ranges(ct_context *h, const ct_batch *img, const double *rot, int64_t rot_stride, int n_rot,
                   int64_t *keys, int64_t keys_stride, int32_t *status) {
     CT_TRY(check_batch(h, img, "images"));
     if (!rot || !keys) return fail(h, CT_E_INVALID, "rot/keys is NULL");
-    RangesArgs a{img_of(img), src_kind(img), vec_ok(img), rot, rot_stride, keys, keys_stride, status};
-    const int nblk = stream_blocks(h, img->npix, img->count, 8);
-    ranges_kernel<<<dim3(nblk, img->count), kThreads, kPipeBytes, h->stream>>>(a);
-    h->launches++;
-    CT_CUDA(h, cudaGetLastError());
+    if (n_rot < 1) return fail(h, CT_E_INVALID, "n_rot must be >= 1");
+    const int nblk = resident_blocks(h, ranges_kernel, kPipeBytes, img->npix, img->count);
+    for (int k0 = 0; k0 < n_rot; k0 += kMaxRot) {  // kMaxRot rotations per pass over the image
+        const int n = n_rot - k0 < kMaxRot ? n_rot - k0 : kMaxRot;
+        RangesArgs a{img_of(img), src_kind(img), vec_ok(img), n, rot + 9 * k0, rot_stride, keys + CT_IDT_KEYS * k0, keys_stride, status};
+        ranges_kernel<<<dim3(nblk, img->count), kThreads, kPipeBytes, h->stream>>>(a);
+        h->launches++;
+        CT_CUDA(h, cudaGetLastError());
+    }
     return CT_OK;
 }
 
@@ -658,8 +685,18 @@ int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt
         a.vec[z] = vec_ok(imgs[z]);
         npix[z] = imgs[z]->npix;
     }
-    // split a budget of ~4 blocks per SM between the two images in proportion to their pixels
-    int64_t budget = ((int64_t)h->sm_count * 4) / B;
+    const size_t smem = (size_t)kPipeBytes + (size_t)((3 * s->bins) << copies_log2_for(s->bins)) * sizeof(unsigned int);
+    // (the pipeline region alone is >= the 3*bins doubles the fused LUT build reuses)
+    if (smem > 48 * 1024 && !h->hist_smem_raised) {
+        CT_CUDA(h, cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        h->hist_smem_raised = true;
+    }
+    // one wave of resident CTAs (persistent, tile-strided), split between the two images in
+    // proportion to their pixels
+    int occ = 0;
+    CT_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hist_kernel, kThreads, smem));
+    if (occ < 1) occ = 1;
+    int64_t budget = ((int64_t)h->sm_count * occ) / B;
     if (budget < 2) budget = 2;
     for (int z = 0; z < 2; ++z) {
         if (!imgs[z]) continue;
@@ -682,12 +719,6 @@ int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt
     CT_TRY(ensure_scratch(h, B));
     a.tickets = h->tickets;
     a.lut = lut_args(s, 0, trace, trace_iter, trace_niter);
-    const size_t smem = (size_t)kPipeBytes + (size_t)3 * (s->bins + 1) * sizeof(double) +
-                        (size_t)((3 * s->bins) << a.copies_log2) * sizeof(unsigned int);  // >= 3*bins doubles for the LUT build
-    if (smem > 48 * 1024 && !h->hist_smem_raised) {
-        CT_CUDA(h, cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        h->hist_smem_raised = true;
-    }
     hist_kernel<<<dim3(a.nblk[0] + a.nblk[1], B), kThreads, smem, h->stream>>>(a);
     h->launches++;
     CT_CUDA(h, cudaGetLastError());
@@ -728,9 +759,7 @@ int launch_remap(ct_context *h, const ct_idt_stage *s, const ct_batch *dst, int 
     a.status = s->status;
     a.bins = s->bins;
     a.round_f32 = round_f32;
-    const int nblk = stream_blocks(h, s->target->npix, s->target->count, 6);
     const size_t smem = (size_t)kPipeBytes + (size_t)9 * CT_IDT_EDGE_STRIDE(s->bins) * sizeof(double);
-    const dim3 grid(nblk, s->target->count);
     switch (a.kind * 2 + a.vec) {
 #define CT_CASE(ID, T, L, V)                                                                                   \
     case ID:                                                                                                   \
@@ -739,7 +768,9 @@ int launch_remap(ct_context *h, const ct_idt_stage *s, const ct_batch *dst, int 
                                             kPipeBytes + 9 * CT_IDT_EDGE_STRIDE(CT_IDT_MAX_BINS) * (int)sizeof(double)));                \
             h->remap_smem_raised[ID] = true;                                                                   \
         }                                                                                                      \
-        remap_kernel<PixelIO<T, L>, V><<<grid, kThreads, smem, h->stream>>>(a);                                \
+        remap_kernel<PixelIO<T, L>, V><<<dim3(resident_blocks(h, remap_kernel<PixelIO<T, L>, V>, smem, s->target->npix, \
+                                                                s->target->count), s->target->count),          \
+                                         kThreads, smem, h->stream>>>(a);                                      \
         break;
         CT_FOR_EACH_SRC(CT_CASE)
 #undef CT_CASE

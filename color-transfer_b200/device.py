@@ -158,8 +158,10 @@ class IdtStages:
     def ranges(self, which):
         h = self.h
         ks, rs = (self.n_iter + 1) * _cabi.CT_IDT_KEYS, self.n_iter * 9
+        # the target's range is needed for iteration 0 only; the reference's for every rotation
         h.check(h.lib.ct_idt_ranges(h.h, self.tb if which == "target" else self.rb, ctypes.c_void_p(self.rot.data_ptr()),
-                                    rs, ctypes.c_void_p(self.keys.data_ptr()), ks, ctypes.c_void_p(self.status.data_ptr())))
+                                    rs, 1 if which == "target" else self.n_iter, ctypes.c_void_p(self.keys.data_ptr()), ks,
+                                    ctypes.c_void_p(self.status.data_ptr())))
 
     def hist(self, it, fuse_lut):
         s = self._stage(it)

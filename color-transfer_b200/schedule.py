@@ -16,7 +16,8 @@ def run_idt_schedule(st, between=None, timer=None, fuse_lut=None):
         fuse_lut = between is None
     tm = timer or (lambda name: contextlib.nullcontext())
     st.init()
-    # K4: the range of iteration 0 needs both images (iterative.py:39-40)
+    # K4: the range of iteration 0 needs both images (iterative.py:39-40); the reference is
+    # static, so ranges("reference") folds its range under EVERY rotation into keys[:, 0..n_iter-1]
     with tm("ranges_target"):
         st.ranges("target")
     with tm("ranges_reference"):
@@ -25,8 +26,7 @@ def run_idt_schedule(st, between=None, timer=None, fuse_lut=None):
         between("keys", st.keys[:, 0])
     for it in range(st.n_iter):
         last = it == st.n_iter - 1
-        # K5 (+K6 when fused).  The reference blocks also fold the reference's range under the
-        # NEXT rotation into keys[:, it + 1].
+        # K5 (+K6 when fused)
         with tm(f"hist_{it}"):
             st.hist(it, fuse_lut)
         if not fuse_lut:

@@ -142,14 +142,15 @@ double ct_idt_value_of(int64_t key);
 
 /* Set n keys to "+inf" so that atomic minima can be folded in. */
 int ct_idt_keys_init(ct_handle h, int64_t *keys, int64_t n);
-/* K4: fold min(p), min(-p) of the projections p = rot @ x (iterative.py:34-35, 39-40) of every
- * pixel of `images` into keys. */
+/* K4: fold min(p), min(-p) of the projections p = rot_k @ x (iterative.py:34-35, 39-40) of every
+ * pixel of `images` into keys, for n_rot consecutive rotations k (rot + 9k -> keys + 6k) in one
+ * pass over the image.  The target needs n_rot = 1 (iteration 0); the reference never changes,
+ * so its range under all n_iter rotations is taken up front. */
 int ct_idt_ranges(ct_handle h, const ct_batch *images, const double *rot, int64_t rot_stride,
-                  int64_t *keys, int64_t keys_stride, int32_t *status);
+                  int32_t n_rot, int64_t *keys, int64_t keys_stride, int32_t *status);
 /* K5: projection + shared-memory-privatised histograms of target and reference on the
- * np.histogram grid (iterative.py:42-43); either image may be NULL.  The reference blocks also
- * fold the reference's range under rot_next into keys_next.  With fuse_lut the last block of
- * each pair runs K6 and clears the counts. */
+ * np.histogram grid (iterative.py:42-43); either image may be NULL.  With fuse_lut the last
+ * block of each pair runs K6 and clears the counts. */
 int ct_idt_hist(ct_handle h, const ct_idt_stage *s, int fuse_lut);
 /* K6: CDFs + inverse-CDF table (iterative.py:45-51); clears counts unless keep_counts. */
 int ct_idt_lut(ct_handle h, const ct_idt_stage *s, int keep_counts);
@@ -169,7 +170,7 @@ typedef struct ct_idt_trace {
 } ct_idt_trace;
 
 size_t ct_idt_workspace_bytes(int64_t npix_target, int32_t count, int32_t bins, int32_t n_iter);
-/* Whole IDT: 2 + 2*n_iter launches.  rotations: dev [B][n_iter][9], drawn by the caller (the
+/* Whole IDT: 3 + 2*n_iter launches (n_iter <= 4).  rotations: dev [B][n_iter][9], drawn by the caller (the
  * Python wrapper calls scipy.stats.special_ortho_group.rvs once per iteration, in order, so the
  * global numpy RNG advances exactly as at iterative.py:32).  `out` must be float64 CT_HWC.
  * workspace may be NULL (the handle then grows its own). */

@@ -42,7 +42,11 @@ class NumpyIdtBackend:
         self.keys[0, slot] = torch.minimum(self.keys[0, slot], torch.from_numpy(mine))
 
     def ranges(self, which):
-        self._fold(0, oracle.project(self.rot[0], self.state if which == "target" else self.ref))
+        if which == "target":
+            self._fold(0, oracle.project(self.rot[0], self.state))
+        else:   # the reference is static: every rotation's range up front
+            for it in range(self.n_iter):
+                self._fold(it, oracle.project(self.rot[it], self.ref))
 
     def _range(self, it):
         k = self.keys[0, it].numpy()
@@ -59,8 +63,6 @@ class NumpyIdtBackend:
             self.counts[0, 0, j] += torch.from_numpy(c_t)
             self.counts[0, 1, j] += torch.from_numpy(c_r)
             self.edges.append(edges)
-        if it + 1 < self.n_iter:
-            self._fold(it + 1, oracle.project(self.rot[it + 1], self.ref))
 
     def lut(self, it):
         c = self.counts[0].numpy()
