@@ -13,7 +13,18 @@
 #ifndef CT_MINB
 #define CT_MINB 2
 #endif
+#ifndef CT_HIST_STAGES
+#define CT_HIST_STAGES 4
+#endif
+#ifndef CT_REMAP_STAGES
+#define CT_REMAP_STAGES 5
+#endif
 namespace ct {
+
+constexpr int kRangesStages = 3, kHistStages = CT_HIST_STAGES, kRemapStages = CT_REMAP_STAGES;
+using RangesPipe = Pipe<kRangesStages>;
+using HistPipe = Pipe<kHistStages>;
+using RemapPipe = Pipe<kRemapStages>;
 
 // ---------------------------------------------------------------------------------------------
 // the shared uniform grid of one axis (np.histogram(bins, range=[lo, hi]))
@@ -128,7 +139,7 @@ struct RangesArgs {
 };
 
 template <typename IO, bool VEC>
-__device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const double *rot, int n_rot, Pipe &pipe,
+__device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const double *rot, int n_rot, RangesPipe &pipe,
                                              int first_block, int nblocks, double (&mn)[kMaxRot][6], bool &bad) {
     using T = typename IO::elem_t;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
@@ -174,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 2) ranges_kernel(RangesArgs a) {
     const int64_t pair = blockIdx.y;
     __shared__ double rot[9 * kMaxRot];
     __shared__ double red[kWarps][6];
-    Pipe pipe(sm_pipe);
+    RangesPipe pipe(sm_pipe);
     if (threadIdx.x == 0) pipe.init();
     if (threadIdx.x < 9 * a.n_rot) rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
     __syncthreads();
@@ -346,7 +357,7 @@ struct HistShared {
 
 template <typename IO, bool VEC, int CL2>  // CL2: log2(copies) when known at compile time, else -1
 __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const HistShared &sh,
-                                           int bins, int copies_log2_rt, unsigned int *hist, Pipe &pipe,
+                                           int bins, int copies_log2_rt, unsigned int *hist, HistPipe &pipe,
                                            int first_block, int nblocks) {
     const int copies_log2 = CL2 >= 0 ? CL2 : copies_log2_rt;
     using T = typename IO::elem_t;
@@ -397,8 +408,8 @@ __global__ void __launch_bounds__(kThreads, 3) hist_kernel(HistArgs a) {
     __shared__ HistShared sh;
     const int64_t pair = blockIdx.y;
     const int bins = a.bins;
-    Pipe pipe(sm_dyn);
-    unsigned int *hist = reinterpret_cast<unsigned int *>(sm_dyn + kPipeBytes / 8);
+    HistPipe pipe(sm_dyn);
+    unsigned int *hist = reinterpret_cast<unsigned int *>(sm_dyn + pipe_bytes(kHistStages) / 8);
     if (threadIdx.x == 0) pipe.init();
     const int z = (int)blockIdx.x < a.nblk[0] ? 0 : 1;
     const int first_block = z == 0 ? blockIdx.x : blockIdx.x - a.nblk[0];
@@ -474,7 +485,7 @@ struct RemapShared {
 
 template <typename SIO, typename DIO, bool VEC, bool NEXT, bool ROUND32>
 __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, const RemapShared &sh,
-                                            const double *tab, Pipe &pipe, double (&mn)[6], bool &bad) {
+                                            const double *tab, RemapPipe &pipe, double (&mn)[6], bool &bad) {
     using TS = typename SIO::elem_t;
     const TS *src = reinterpret_cast<const TS *>(a.src.data) + pair * a.src.image_stride;
     double *dst = reinterpret_cast<double *>(a.dst.data) + pair * a.dst.image_stride;
@@ -542,7 +553,7 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
 // block-uniform runtime switches inside
 template <typename SIO, bool VEC>
 __device__ __forceinline__ void remap_dispatch(const RemapArgs &a, int64_t pair, const RemapShared &sh,
-                                               const double *tab, Pipe &pipe, bool next, double (&mn)[6], bool &bad) {
+                                               const double *tab, RemapPipe &pipe, bool next, double (&mn)[6], bool &bad) {
     using StateIO = PixelIO<double, CT_CHW>;
     using FinalIO = PixelIO<double, CT_HWC>;
     if (a.round_f32) {  // iteration 0 of float32 input: the state buffer is always the destination or n_iter == 1
@@ -566,8 +577,8 @@ template <typename SIO, bool VEC>
 __global__ void __launch_bounds__(kThreads, CT_MINB) remap_kernel(RemapArgs a) {
     extern __shared__ __align__(16) double sm_remap[];  // tile pipeline | edges + {fp, slope} entries of the three axes
     __shared__ RemapShared sh;
-    Pipe pipe(sm_remap);
-    double *sm_tab = sm_remap + kPipeBytes / 8;
+    RemapPipe pipe(sm_remap);
+    double *sm_tab = sm_remap + pipe_bytes(kRemapStages) / 8;
     if (threadIdx.x == 0) pipe.init();
     const int64_t pair = blockIdx.y;
     const int bins = a.bins;
@@ -606,13 +617,6 @@ static int resident_blocks(const ct_context *h, K kernel, size_t smem, int64_t n
     return (int)(n < 1 ? 1 : n);
 }
 
-static int stream_blocks(const ct_context *h, int64_t npix, int64_t units, int per_sm) {
-    const int64_t want = (npix / 2 + kThreads - 1) / kThreads;
-    int64_t cap = ((int64_t)h->sm_count * per_sm) / (units > 0 ? units : 1);
-    if (cap < 1) cap = 1;
-    const int64_t n = want < cap ? want : cap;
-    return (int)(n < 1 ? 1 : n);
-}
 
 int launch_keys_init(ct_context *h, int64_t *keys, int64_t n) {
     if (!keys || n <= 0) return fail(h, CT_E_INVALID, "bad keys_init arguments");
@@ -627,11 +631,11 @@ int launch_ranges(ct_context *h, const ct_batch *img, const double *rot, int64_t
     CT_TRY(check_batch(h, img, "images"));
     if (!rot || !keys) return fail(h, CT_E_INVALID, "rot/keys is NULL");
     if (n_rot < 1) return fail(h, CT_E_INVALID, "n_rot must be >= 1");
-    const int nblk = resident_blocks(h, ranges_kernel, kPipeBytes, img->npix, img->count);
+    const int nblk = resident_blocks(h, ranges_kernel, pipe_bytes(kRangesStages), img->npix, img->count);
     for (int k0 = 0; k0 < n_rot; k0 += kMaxRot) {  // kMaxRot rotations per pass over the image
         const int n = n_rot - k0 < kMaxRot ? n_rot - k0 : kMaxRot;
         RangesArgs a{img_of(img), src_kind(img), vec_ok(img), n, rot + 9 * k0, rot_stride, keys + CT_IDT_KEYS * k0, keys_stride, status};
-        ranges_kernel<<<dim3(nblk, img->count), kThreads, kPipeBytes, h->stream>>>(a);
+        ranges_kernel<<<dim3(nblk, img->count), kThreads, pipe_bytes(kRangesStages), h->stream>>>(a);
         h->launches++;
         CT_CUDA(h, cudaGetLastError());
     }
@@ -685,10 +689,10 @@ int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt
         a.vec[z] = vec_ok(imgs[z]);
         npix[z] = imgs[z]->npix;
     }
-    const size_t smem = (size_t)kPipeBytes + (size_t)((3 * s->bins) << copies_log2_for(s->bins)) * sizeof(unsigned int);
+    const size_t smem = (size_t)pipe_bytes(kHistStages) + (size_t)((3 * s->bins) << copies_log2_for(s->bins)) * sizeof(unsigned int);
     // (the pipeline region alone is >= the 3*bins doubles the fused LUT build reuses)
     if (smem > 48 * 1024 && !h->hist_smem_raised) {
-        CT_CUDA(h, cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CT_CUDA(h, cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
         h->hist_smem_raised = true;
     }
     // one wave of resident CTAs (persistent, tile-strided), split between the two images in
@@ -759,13 +763,13 @@ int launch_remap(ct_context *h, const ct_idt_stage *s, const ct_batch *dst, int 
     a.status = s->status;
     a.bins = s->bins;
     a.round_f32 = round_f32;
-    const size_t smem = (size_t)kPipeBytes + (size_t)9 * CT_IDT_EDGE_STRIDE(s->bins) * sizeof(double);
+    const size_t smem = (size_t)pipe_bytes(kRemapStages) + (size_t)9 * CT_IDT_EDGE_STRIDE(s->bins) * sizeof(double);
     switch (a.kind * 2 + a.vec) {
 #define CT_CASE(ID, T, L, V)                                                                                   \
     case ID:                                                                                                   \
         if (smem > 40 * 1024 && !h->remap_smem_raised[ID]) {                                                   \
             CT_CUDA(h, cudaFuncSetAttribute(remap_kernel<PixelIO<T, L>, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            kPipeBytes + 9 * CT_IDT_EDGE_STRIDE(CT_IDT_MAX_BINS) * (int)sizeof(double)));                \
+                                            pipe_bytes(kRemapStages) + 9 * CT_IDT_EDGE_STRIDE(CT_IDT_MAX_BINS) * (int)sizeof(double)));                \
             h->remap_smem_raised[ID] = true;                                                                   \
         }                                                                                                      \
         remap_kernel<PixelIO<T, L>, V><<<dim3(resident_blocks(h, remap_kernel<PixelIO<T, L>, V>, smem, s->target->npix, \

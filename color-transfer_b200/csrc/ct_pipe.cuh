@@ -14,9 +14,8 @@
 
 namespace ct {
 
-constexpr int kStages = 3;
 constexpr int kTileBytes = kThreads * 48;  // 12 KB for every (dtype, layout)
-constexpr int kPipeBytes = kStages * kTileBytes + 2 * kStages * 8;
+constexpr int pipe_bytes(int stages) { return stages * kTileBytes + 2 * stages * 8; }  // a multiple of 16 B
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -49,7 +48,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 // Shared-memory view of one CTA's pipeline (carved from dynamic shared memory, 16 B aligned).
+template <int kStages>
 struct Pipe {
+    static constexpr int kNumStages = kStages;
     unsigned char *stage;  // kStages * kTileBytes
     uint64_t *full;        // [kStages]
     uint64_t *empty;       // [kStages]
@@ -71,10 +72,11 @@ struct Pipe {
 // Runs f(raw, first_pixel_of_group) on every pixel group of the FULL tiles first_tile, first_tile + tile_stride, ...
 // of one image; every thread of the CTA must call it (block-uniform trip count).  `pipe` must be
 // freshly initialised (phase 0) for each call.
-template <typename IO, typename F>
-__device__ __forceinline__ void pipe_for_each_group(Pipe &pipe, const typename IO::elem_t *img, int64_t plane,
+template <typename IO, typename P, typename F>
+__device__ __forceinline__ void pipe_for_each_group(P &pipe, const typename IO::elem_t *img, int64_t plane,
                                                     int ntiles, int first_tile, int tile_stride, F &&f) {
     using T = typename IO::elem_t;
+    constexpr int kStages = P::kNumStages;
     constexpr int G = IO::G;
     constexpr int kTilePx = kThreads * G;
     const int mine = first_tile < ntiles ? (ntiles - first_tile + tile_stride - 1) / tile_stride : 0;
