@@ -110,6 +110,13 @@ struct PixelIO {
 #pragma unroll
             for (int c = 0; c < 3; ++c) x[i][c] = (double)(LAYOUT == CT_HWC ? r.e[3 * i + c] : r.e[c * G + i]);
     }
+    // the same pixels as floats (exact for float images): seeds / statistics of the Lab path
+    __device__ __forceinline__ static void unpack_f(const Raw &r, float (&x)[G][3]) {
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) x[i][c] = (float)(LAYOUT == CT_HWC ? r.e[3 * i + c] : r.e[c * G + i]);
+    }
     template <bool VEC>
     __device__ __forceinline__ static void load(const T *img, int64_t plane, int64_t g, double (&x)[G][3]) {
         unpack(load_raw<VEC>(img, plane, (int)g), x);

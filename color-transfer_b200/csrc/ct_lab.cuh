@@ -1,11 +1,19 @@
 // sRGB <-> CIE-Lab (D65, 2 degree) per-pixel math, the published scikit-image algorithm that
 // the reference calls at methods/linear.py:25,26,40 (rgb2xyz, xyz2lab, _lab2xyz, xyz2rgb).
 //
-// The three fractional powers (x^2.4, cbrt, x^(1/2.4)) are the cost of this path.  Each one is
-// seeded with MUFU lg2/ex2 in fp32 (relative error ~3e-7) and polished by ONE Newton step whose
-// residual is evaluated in fp64 with an FMA, which squares the error (~1e-12): fp64-grade
-// results for ~10 DP instructions instead of the ~150 of pow().  The division inside the
-// Newton step only scales an already tiny correction, so it is an fp32 reciprocal.
+// The three fractional powers (x^2.4, cbrt, x^(1/2.4)) are the cost of this path, and on B200
+// the scarce unit is the XU pipe (MUFU and every F2F/I2F conversion: 16 lanes/clk/SM, a quarter
+// of the fp64 rate).  Each power is therefore computed as
+//     seed   y0 ~ x^(-1/n) from MUFU lg2/ex2 on an fp32 "shadow" of the operand  (2 XU ops)
+//     polish one DIVISION-FREE Newton step for y = x^(-1/n) in fp64:
+//            y = y0 * ((n+1) - x*y0^n) / n          error (n+1)/2 * e0^2 ~ 1e-12  (1 XU op: y0 -> double)
+//     result x^2.4 = (x*y)^3 (n=5),  cbrt x = x*y^2 (n=3),  x^(5/12) = x*y^7 (n=12)
+// i.e. 3 XU operations per power instead of 7 (pow() would be ~150 fp64 instructions).  The
+// shadow chain (the same formulas in fp32, only ever used to seed) keeps every intermediate
+// available as a float without converting doubles back.
+//
+// The statistics pass (mean / std over millions of pixels) uses the fp32 chain alone: its
+// per-pixel error (~3e-7 relative) shifts the Lab means by ~1e-5 of a Lab unit, 1e-7 in RGB.
 #pragma once
 
 #include "ct_common.cuh"
@@ -23,90 +31,125 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// u^2.4 for u > 0:  u^2 * w,  w = u^0.4 solves w^5 = u^2.
-__device__ __forceinline__ double pow_2p4(double u) {
-    const double u2 = u * u;
-    const float w0 = ex2_approx(0.4f * lg2_approx((float)u));
-    const double w = (double)w0;
-    const double w2 = w * w, w4 = w2 * w2;
-    const double resid = fma(w4, w, -u2);                // w^5 - u^2
-    const float inv = 0.2f * rcp_approx((float)w4);      // 1 / (5 w^4)
-    return u2 * fma(-resid, (double)inv, w);
-}
-
-// t^(1/3) for t > 0:  c solves c^3 = t.
-__device__ __forceinline__ double cbrt_pos(double t) {
-    const float c0 = ex2_approx(0.33333334f * lg2_approx((float)t));
-    const double c = (double)c0;
-    const double c2 = c * c;
-    const double resid = fma(c2, c, -t);                 // c^3 - t
-    const float inv = 0.33333334f * rcp_approx(c0 * c0); // 1 / (3 c^2)
-    return fma(-resid, (double)inv, c);
-}
-
-// c^(1/2.4) = c^(5/12) for c > 0:  v solves v^12 = c^5.
-__device__ __forceinline__ double pow_5_12(double c) {
-    const float v0 = ex2_approx(0.41666666f * lg2_approx((float)c));
-    const double v = (double)v0;
-    const double v2 = v * v, v4 = v2 * v2, v8 = v4 * v4;
-    const double c2 = c * c, c5 = c2 * c2 * c;
-    const double resid = fma(v8, v4, -c5);               // v^12 - c^5
-    const float v2f = v0 * v0, v4f = v2f * v2f, v8f = v4f * v4f;
-    const float inv = 0.083333336f * rcp_approx(v8f * v2f * v0);  // 1 / (12 v^11)
-    return fma(-resid, (double)inv, v);
-}
 
 // xyz_from_rgb with each row divided by the D65 white (0.95047, 1, 1.08883)
-__device__ __forceinline__ void rgb2lab(const double (&rgb)[3], double (&out)[3]) {
-    double lin[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const double v = rgb[c];
-        lin[c] = v > 0.04045 ? pow_2p4((v + 0.055) * (1.0 / 1.055)) : v * (1.0 / 12.92);
+#define CT_XYZ_ROW0(T, a, b, c) ((T)(0.412453 / 0.95047) * (a) + (T)(0.357580 / 0.95047) * (b) + (T)(0.180423 / 0.95047) * (c))
+#define CT_XYZ_ROW1(T, a, b, c) ((T)0.212671 * (a) + (T)0.715160 * (b) + (T)0.072169 * (c))
+#define CT_XYZ_ROW2(T, a, b, c) ((T)(0.019334 / 1.08883) * (a) + (T)(0.119193 / 1.08883) * (b) + (T)(0.950227 / 1.08883) * (c))
+
+// ------------------------------------------------------------------ fp32 chain (statistics, seeds)
+__device__ __forceinline__ float srgb_decode_f(float v) {
+    return v > 0.04045f ? ex2_approx(2.4f * lg2_approx((v + 0.055f) * (1.0f / 1.055f))) : v * (1.0f / 12.92f);
+}
+__device__ __forceinline__ float lab_f_f(float t) {
+    return t > 0.008856f ? ex2_approx(0.33333334f * lg2_approx(t)) : fmaf(7.787f, t, 16.0f / 116.0f);
+}
+__device__ __forceinline__ void rgb2lab_f32(const float (&rgb)[3], float (&out)[3]) {
+    const float l0 = srgb_decode_f(rgb[0]), l1 = srgb_decode_f(rgb[1]), l2 = srgb_decode_f(rgb[2]);
+    const float fx = lab_f_f(CT_XYZ_ROW0(float, l0, l1, l2));
+    const float fy = lab_f_f(CT_XYZ_ROW1(float, l0, l1, l2));
+    const float fz = lab_f_f(CT_XYZ_ROW2(float, l0, l1, l2));
+    out[0] = fmaf(116.0f, fy, -16.0f);
+    out[1] = 500.0f * (fx - fy);
+    out[2] = 200.0f * (fy - fz);
+}
+
+// ------------------------------------------------------------------ fp64 chain with fp32 shadow
+// Every function takes the operand as (double x, float xf ~ x) and returns (double r, float rf ~ r).
+
+// ((v + 0.055) / 1.055)^2.4 for v > 0.04045, else v / 12.92
+__device__ __forceinline__ double srgb_decode(double v, float vf, float &rf) {
+    if (v > 0.04045) {
+        const double u = (v + 0.055) * (1.0 / 1.055);
+        const float uf = (vf + 0.055f) * (1.0f / 1.055f);
+        const float y0 = ex2_approx(-0.2f * lg2_approx(uf));   // u^(-1/5)
+        double y = (double)y0;
+        const double y2 = y * y, y4 = y2 * y2;
+        y *= fma(-(u * y4) * y, 0.2, 1.2);                     // y (6 - u y^5) / 5
+        const double uy = u * y;                               // u^(4/5)
+        const float uyf = uf * y0;
+        rf = uyf * uyf * uyf;
+        return uy * uy * uy;
     }
-    const double x = (0.412453 / 0.95047) * lin[0] + (0.357580 / 0.95047) * lin[1] + (0.180423 / 0.95047) * lin[2];
-    const double y = 0.212671 * lin[0] + 0.715160 * lin[1] + 0.072169 * lin[2];
-    const double z = (0.019334 / 1.08883) * lin[0] + (0.119193 / 1.08883) * lin[1] + (0.950227 / 1.08883) * lin[2];
-    const double fx = x > 0.008856 ? cbrt_pos(x) : fma(7.787, x, 16.0 / 116.0);
-    const double fy = y > 0.008856 ? cbrt_pos(y) : fma(7.787, y, 16.0 / 116.0);
-    const double fz = z > 0.008856 ? cbrt_pos(z) : fma(7.787, z, 16.0 / 116.0);
+    rf = vf * (1.0f / 12.92f);
+    return v * (1.0 / 12.92);
+}
+
+// cbrt(t) for t > 0.008856, else 7.787 t + 16/116
+__device__ __forceinline__ double lab_f(double t, float tf, float &rf) {
+    if (t > 0.008856) {
+        const float y0 = ex2_approx(-0.33333334f * lg2_approx(tf));  // t^(-1/3)
+        double y = (double)y0;
+        y *= fma(-(t * y) * (y * y), 1.0 / 3.0, 4.0 / 3.0);          // y (4 - t y^3) / 3
+        rf = tf * (y0 * y0);
+        return t * (y * y);
+    }
+    rf = fmaf(7.787f, tf, 16.0f / 116.0f);
+    return fma(7.787, t, 16.0 / 116.0);
+}
+
+__device__ __forceinline__ void rgb2lab(const double (&rgb)[3], const float (&rgbf)[3], double (&out)[3], float (&outf)[3]) {
+    float lf[3];
+    double l[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) l[c] = srgb_decode(rgb[c], rgbf[c], lf[c]);
+    float fxf, fyf, fzf;
+    const double fx = lab_f(CT_XYZ_ROW0(double, l[0], l[1], l[2]), CT_XYZ_ROW0(float, lf[0], lf[1], lf[2]), fxf);
+    const double fy = lab_f(CT_XYZ_ROW1(double, l[0], l[1], l[2]), CT_XYZ_ROW1(float, lf[0], lf[1], lf[2]), fyf);
+    const double fz = lab_f(CT_XYZ_ROW2(double, l[0], l[1], l[2]), CT_XYZ_ROW2(float, lf[0], lf[1], lf[2]), fzf);
     out[0] = fma(116.0, fy, -16.0);
     out[1] = 500.0 * (fx - fy);
     out[2] = 200.0 * (fy - fz);
+    outf[0] = fmaf(116.0f, fyf, -16.0f);
+    outf[1] = 500.0f * (fxf - fyf);
+    outf[2] = 200.0f * (fyf - fzf);
 }
 
 // scipy.linalg.inv(xyz_from_rgb) (what skimage computes at import), columns pre-multiplied by
 // the D65 white so that rgb = m @ (finv(fx), finv(fy), finv(fz)).
-__device__ __forceinline__ double rgb_from_f(int c, double X, double Y, double Z) {
-    constexpr double m[9] = {3.079980302271805,   -1.5371515162713183,  -0.5428213080224701,
-                             -0.9212477523232383, 1.8759900014898907,   0.045247339514465995,
-                             0.05289046109881184, -0.20404133836651123, 1.1512320119619401};
-    return m[3 * c + 0] * X + m[3 * c + 1] * Y + m[3 * c + 2] * Z;
-}
+#define CT_RGB_ROW(T, c, X, Y, Z)                                                                       \
+    ((c) == 0 ? (T)3.079980302271805 * (X) + (T)-1.5371515162713183 * (Y) + (T)-0.5428213080224701 * (Z) \
+     : (c) == 1 ? (T)-0.9212477523232383 * (X) + (T)1.8759900014898907 * (Y) + (T)0.045247339514465995 * (Z) \
+                : (T)0.05289046109881184 * (X) + (T)-0.20404133836651123 * (Y) + (T)1.1512320119619401 * (Z))
 
 __device__ __forceinline__ double finv(double f) {
     return f > 0.2068966 ? f * f * f : (f - 16.0 / 116.0) * (1.0 / 7.787);
 }
-__device__ __forceinline__ double gamma_encode(double c) {
-    const double s = c > 0.0031308 ? fma(1.055, pow_5_12(c), -0.055) : 12.92 * c;
-    double s2 = s < 0.0 ? 0.0 : s;  // np.clip(arr, 0, 1); NaN stays NaN
-    return s2 > 1.0 ? 1.0 : s2;
+__device__ __forceinline__ float finv_f(float f) {
+    return f > 0.2068966f ? f * f * f : (f - 16.0f / 116.0f) * (1.0f / 7.787f);
 }
 
-__device__ __forceinline__ void lab2rgb(const double (&labv)[3], double (&rgb)[3]) {
+// 1.055 c^(1/2.4) - 0.055 for c > 0.0031308, else 12.92 c; then np.clip(., 0, 1)
+__device__ __forceinline__ double srgb_encode(double c, float cf) {
+    double s;
+    if (c > 0.0031308) {
+        const float y0 = ex2_approx(-0.083333336f * lg2_approx(cf));  // c^(-1/12)
+        double y = (double)y0;
+        double y2 = y * y, y4 = y2 * y2;
+        const double y12 = (y4 * y4) * y4;
+        y *= fma(-c * y12, 1.0 / 12.0, 13.0 / 12.0);                   // y (13 - c y^12) / 12
+        y2 = y * y;
+        y4 = y2 * y2;
+        s = fma(1.055, c * ((y4 * y2) * y), -0.055);                    // c y^7 = c^(5/12)
+    } else {
+        s = 12.92 * c;
+    }
+    s = s < 0.0 ? 0.0 : s;  // NaN stays NaN, like np.clip
+    return s > 1.0 ? 1.0 : s;
+}
+
+__device__ __forceinline__ void lab2rgb(const double (&labv)[3], const float (&labf)[3], double (&rgb)[3]) {
     const double fy = (labv[0] + 16.0) * (1.0 / 116.0);
     const double fx = fma(labv[1], 1.0 / 500.0, fy);
     double fz = fma(labv[2], -1.0 / 200.0, fy);
     fz = fz < 0.0 ? 0.0 : fz;  // skimage zeroes invalid z (and warns)
+    const float fyf = (labf[0] + 16.0f) * (1.0f / 116.0f);
+    const float fxf = fmaf(labf[1], 1.0f / 500.0f, fyf);
+    const float fzf = fmaxf(fmaf(labf[2], -1.0f / 200.0f, fyf), 0.0f);
     const double X = finv(fx), Y = finv(fy), Z = finv(fz);
+    const float Xf = finv_f(fxf), Yf = finv_f(fyf), Zf = finv_f(fzf);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) rgb[c] = gamma_encode(rgb_from_f(c, X, Y, Z));
+    for (int c = 0; c < 3; ++c) rgb[c] = srgb_encode(CT_RGB_ROW(double, c, X, Y, Z), CT_RGB_ROW(float, c, Xf, Yf, Zf));
 }
 
 }  // namespace lab

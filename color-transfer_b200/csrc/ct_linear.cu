@@ -27,11 +27,15 @@ struct MomentsArgs {
 };
 
 template <bool LAB>
-__device__ __forceinline__ void accumulate(const double (&rgb)[3], double (&acc)[9]) {
+__device__ __forceinline__ void accumulate(const double (&rgb)[3], const float (&rgbf)[3], double (&acc)[9]) {
     double v[3];
     if (LAB) {
-        lab::rgb2lab(rgb, v);
-        v[0] -= 50.0;
+        // statistics only: the fp32 Lab chain (ct_lab.cuh), accumulated in fp64
+        float labf[3];
+        lab::rgb2lab_f32(rgbf, labf);
+        v[0] = (double)(labf[0] - 50.0f);
+        v[1] = (double)labf[1];
+        v[2] = (double)labf[2];
     } else {
         v[0] = rgb[0] - 0.5;
         v[1] = rgb[1] - 0.5;
@@ -58,16 +62,19 @@ __device__ __forceinline__ void moments_image(const Img &im, int64_t pair, doubl
     const int64_t ngroups = im.npix / G;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += stride) {
+        const typename IO::Raw raw = IO::template load_raw<VEC>(base, im.plane_stride, (int)g);
         double x[G][3];
-        IO::template load<VEC>(base, im.plane_stride, g, x);
+        float xf[G][3];
+        if (LAB) IO::unpack_f(raw, xf); else IO::unpack(raw, x);
 #pragma unroll
-        for (int i = 0; i < G; ++i) accumulate<LAB>(x[i], acc);
+        for (int i = 0; i < G; ++i) accumulate<LAB>(x[i], xf[i], acc);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int64_t p = ngroups * G; p < im.npix; ++p) {
+    if (blockIdx.x == 0) {
+        for (int64_t p = ngroups * G + threadIdx.x; p < im.npix; p += kThreads) {
             double x[3];
             IO::load1(base, im.plane_stride, p, x);
-            accumulate<LAB>(x, acc);
+            const float xf[3] = {(float)x[0], (float)x[1], (float)x[2]};
+            accumulate<LAB>(x, xf, acc);
         }
     }
 }
@@ -167,15 +174,20 @@ struct ApplyArgs {
 };
 
 template <bool LAB>
-__device__ __forceinline__ void apply_pixel(const double *xf, const double (&x)[3], double (&y)[3]) {
-    if (LAB) {
+__device__ __forceinline__ void apply_pixel(const double *xf, const float *xff, const double (&x)[3],
+                                            const float (&xs)[3], double (&y)[3]) {
+    if (LAB) {  // xs / xff: fp32 shadows of the pixel and the transform, seeds only
         double l[3], m[3];
-        lab::rgb2lab(x, l);
+        float lf[3], mf[3];
+        lab::rgb2lab(x, xs, l, lf);
         // (lab - mean_t) * std_r / std_t + mean_r   (linear.py:38)
         m[0] = fma(l[0] - xf[9], xf[0], xf[12]);
         m[1] = fma(l[1] - xf[10], xf[4], xf[13]);
         m[2] = fma(l[2] - xf[11], xf[8], xf[14]);
-        lab::lab2rgb(m, y);
+        mf[0] = fmaf(lf[0] - xff[9], xff[0], xff[12]);
+        mf[1] = fmaf(lf[1] - xff[10], xff[4], xff[13]);
+        mf[2] = fmaf(lf[2] - xff[11], xff[8], xff[14]);
+        lab::lab2rgb(m, mf, y);
     } else {
         const double d0 = x[0] - xf[9], d1 = x[1] - xf[10], d2 = x[2] - xf[11];
 #pragma unroll
@@ -189,7 +201,11 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(ApplyArgs a) {
     using TD = typename DIO::elem_t;
     const int64_t pair = blockIdx.y;
     __shared__ double xf[CT_XFORM_DOUBLES];
-    if (threadIdx.x < CT_XFORM_DOUBLES) xf[threadIdx.x] = a.xform[pair * CT_XFORM_DOUBLES + threadIdx.x];
+    __shared__ float xff[CT_XFORM_DOUBLES];
+    if (threadIdx.x < CT_XFORM_DOUBLES) {
+        xf[threadIdx.x] = a.xform[pair * CT_XFORM_DOUBLES + threadIdx.x];
+        xff[threadIdx.x] = (float)xf[threadIdx.x];
+    }
     __syncthreads();
     const TS *src = reinterpret_cast<const TS *>(a.src.data) + pair * a.src.image_stride;
     TD *dst = reinterpret_cast<TD *>(a.dst.data) + pair * a.dst.image_stride;
@@ -197,17 +213,21 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(ApplyArgs a) {
     const int64_t ngroups = a.src.npix / G;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += stride) {
+        const typename SIO::Raw raw = SIO::template load_raw<VEC>(src, a.src.plane_stride, (int)g);
         double x[G][3], y[G][3];
-        SIO::template load<VEC>(src, a.src.plane_stride, g, x);
+        float xs[G][3];
+        SIO::unpack(raw, x);
+        if (LAB) SIO::unpack_f(raw, xs);
 #pragma unroll
-        for (int i = 0; i < G; ++i) apply_pixel<LAB>(xf, x[i], y[i]);
+        for (int i = 0; i < G; ++i) apply_pixel<LAB>(xf, xff, x[i], xs[i], y[i]);
         DIO::template store<VEC, G>(dst, a.dst.plane_stride, g * G, y);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int64_t p = ngroups * G; p < a.src.npix; ++p) {
+    if (blockIdx.x == 0) {
+        for (int64_t p = ngroups * G + threadIdx.x; p < a.src.npix; p += kThreads) {
             double x[3], y[3];
             SIO::load1(src, a.src.plane_stride, p, x);
-            apply_pixel<LAB>(xf, x, y);
+            const float xs[3] = {(float)x[0], (float)x[1], (float)x[2]};
+            apply_pixel<LAB>(xf, xff, x, xs, y);
             DIO::store1(dst, a.dst.plane_stride, p, y);
         }
     }
