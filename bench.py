@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--kernels-only", action="store_true", help="profiling aid: only the timed device steps")
+    ap.add_argument("--linear-only", action="store_true", help="profiling aid: only the linear-transfer extras")
     return ap.parse_args()
 
 
@@ -260,6 +261,10 @@ def main():
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    if a.linear_only:
+        print(json.dumps(linear_extras(torch, device, synth, _cabi, handle, dev, measured_peaks()[0])))
+        return
 
     # frames k = rank, rank + world, ...: rotations pre-drawn in frame order after seed 42
     np.random.seed(42)

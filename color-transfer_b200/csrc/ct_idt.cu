@@ -24,6 +24,8 @@ namespace ct {
 constexpr int kRangesStages = 3, kHistStages = CT_HIST_STAGES, kRemapStages = CT_REMAP_STAGES;
 using RangesPipe = Pipe<kRangesStages>;
 using HistPipe = Pipe<kHistStages>;
+// hist kernel dynamic shared memory: stages + two barrier sets (one per image), then the histograms
+constexpr int kHistSmemFront = kHistStages * kTileBytes + 2 * (2 * kHistStages * 8);
 using RemapPipe = Pipe<kRemapStages>;
 
 // ---------------------------------------------------------------------------------------------
@@ -256,15 +258,36 @@ __device__ void build_lut(const LutArgs &a, int64_t pair, double *sm) {
             if (a.tr_cr) a.tr_cr[(tr_base + j) * bins + k] = (int64_t)cr;
         }
         __syncthreads();
-        if (threadIdx.x < 2) {  // p.cumsum().astype(float); cp /= cp[-1]  (integers < 2^53: exact)
-            double *c = threadIdx.x == 0 ? cdf_t : cdf_r;
-            double run = 0.0;
-            for (int k = 0; k < bins; ++k) {
+        // p.cumsum().astype(float); cp /= cp[-1].  The counts are integers below 2^53, so the
+        // running sums are exact in any order: warp 0 scans the target, warp 1 the reference,
+        // each lane owning a contiguous chunk; the IEEE division then runs on all threads.
+        if (threadIdx.x < 64) {
+            double *c = threadIdx.x < 32 ? cdf_t : cdf_r;
+            const int lane = threadIdx.x & 31;
+            const int chunk = (bins + 31) / 32;
+            const int k0 = lane * chunk, k1 = min(k0 + chunk, bins);
+            double mine = 0.0;
+            for (int k = k0; k < k1; ++k) mine += c[k];
+            double incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            double run = incl - mine;
+            for (int k = k0; k < k1; ++k) {
                 run += c[k];
                 c[k] = run;
             }
-            const double total = run;
-            for (int k = 0; k < bins; ++k) c[k] = div_rn(c[k], total);
+        }
+        __syncthreads();
+        {
+            const double total_t = cdf_t[bins - 1], total_r = cdf_r[bins - 1];
+            __syncthreads();
+            for (int k = threadIdx.x; k < bins; k += kThreads) {
+                cdf_t[k] = div_rn(cdf_t[k], total_t);
+                cdf_r[k] = div_rn(cdf_r[k], total_r);
+            }
         }
         __syncthreads();
         // f = np.interp(cdf_t, cdf_r, edges[1:])
@@ -403,47 +426,52 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Hi
 }
 
 __global__ void __launch_bounds__(kThreads, 3) hist_kernel(HistArgs a) {
-    // tile pipeline | histograms; the front is later reused by the LUT build
+    // tile pipeline (stages, then one barrier set per image) | histograms; the front is later
+    // reused by the LUT build
     extern __shared__ __align__(16) double sm_dyn[];
     __shared__ HistShared sh;
     const int64_t pair = blockIdx.y;
     const int bins = a.bins;
-    HistPipe pipe(sm_dyn);
-    unsigned int *hist = reinterpret_cast<unsigned int *>(sm_dyn + pipe_bytes(kHistStages) / 8);
-    if (threadIdx.x == 0) pipe.init();
-    const int z = (int)blockIdx.x < a.nblk[0] ? 0 : 1;
-    const int first_block = z == 0 ? blockIdx.x : blockIdx.x - a.nblk[0];
-
+    unsigned int *hist = reinterpret_cast<unsigned int *>(sm_dyn + kHistSmemFront / 8);
     if (threadIdx.x < 9) sh.rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
     if (threadIdx.x >= 32 && threadIdx.x < 35) {
         bool finite;
         sh.grid[threadIdx.x - 32] = grid_from_keys(a.keys + pair * a.keys_stride, threadIdx.x - 32, bins, finite);
     }
     const int nslots = (3 * bins) << a.copies_log2;
-    for (int i = threadIdx.x; i < nslots; i += kThreads) hist[i] = 0u;
-    __syncthreads();
+    const int copies = 1 << a.copies_log2;
 
-    const int sel = a.kind[z] * 2 + a.vec[z];
+    // Every CTA takes its 1/gridDim.x share of the target tiles and then of the reference tiles:
+    // identical work per CTA whatever the two images' sizes and dtypes are (a static split of the
+    // CTAs between the images is unbalanced as soon as their bytes per pixel differ).
+    for (int z = 0; z < 2; ++z) {
+        if (!a.nblk[z]) continue;  // this image is absent (stage API)
+        HistPipe pipe(sm_dyn, z);
+        if (threadIdx.x == 0) pipe.init();
+        for (int i = threadIdx.x; i < nslots; i += kThreads) hist[i] = 0u;
+        __syncthreads();
+        const int sel = a.kind[z] * 2 + a.vec[z];
 #define CT_HIST_CALL(T, L, V, CL2V) \
-    hist_image<PixelIO<T, L>, V, CL2V>(a.img[z], pair, sh, bins, a.copies_log2, hist, pipe, first_block, a.nblk[z])
+    hist_image<PixelIO<T, L>, V, CL2V>(a.img[z], pair, sh, bins, a.copies_log2, hist, pipe, blockIdx.x, gridDim.x)
 #define CT_CASE_3(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, 3); break;
 #define CT_CASE_g(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, -1); break;
-    if (a.copies_log2 == 3) {  // bins <= 256: the default 255
-        switch (sel) { CT_FOR_EACH_SRC(CT_CASE_3) }
-    } else {
-        switch (sel) { CT_FOR_EACH_SRC(CT_CASE_g) }
-    }
+        if (a.copies_log2 == 3) {  // bins <= 256: the default 255
+            switch (sel) { CT_FOR_EACH_SRC(CT_CASE_3) }
+        } else {
+            switch (sel) { CT_FOR_EACH_SRC(CT_CASE_g) }
+        }
 #undef CT_HIST_CALL
 #undef CT_CASE_3
 #undef CT_CASE_g
-    __syncthreads();
-    // flush: sum the copies of each bin, one 64-bit integer atomic per non-empty bin
-    uint64_t *cnt = a.counts + (pair * 2 + z) * 3 * (int64_t)bins;
-    const int copies = 1 << a.copies_log2;
-    for (int i = threadIdx.x; i < 3 * bins; i += kThreads) {
-        unsigned int s = 0;
-        for (int c = 0; c < copies; ++c) s += hist[(i << a.copies_log2) + c];
-        if (s) atomicAdd(reinterpret_cast<unsigned long long *>(cnt + i), (unsigned long long)s);
+        __syncthreads();
+        // flush: sum the copies of each bin, one 64-bit integer atomic per non-empty bin
+        uint64_t *cnt = a.counts + (pair * 2 + z) * 3 * (int64_t)bins;
+        for (int i = threadIdx.x; i < 3 * bins; i += kThreads) {
+            unsigned int s = 0;
+            for (int c = 0; c < copies; ++c) s += hist[(i << a.copies_log2) + c];
+            if (s) atomicAdd(reinterpret_cast<unsigned long long *>(cnt + i), (unsigned long long)s);
+        }
+        __syncthreads();
     }
     if (!a.fuse_lut) return;
     __threadfence();
@@ -689,26 +717,22 @@ int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt
         a.vec[z] = vec_ok(imgs[z]);
         npix[z] = imgs[z]->npix;
     }
-    const size_t smem = (size_t)pipe_bytes(kHistStages) + (size_t)((3 * s->bins) << copies_log2_for(s->bins)) * sizeof(unsigned int);
+    const size_t smem = (size_t)kHistSmemFront + (size_t)((3 * s->bins) << copies_log2_for(s->bins)) * sizeof(unsigned int);
     // (the pipeline region alone is >= the 3*bins doubles the fused LUT build reuses)
     if (smem > 48 * 1024 && !h->hist_smem_raised) {
         CT_CUDA(h, cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
         h->hist_smem_raised = true;
     }
-    // one wave of resident CTAs (persistent, tile-strided), split between the two images in
-    // proportion to their pixels
+    // one wave of resident CTAs per launch (persistent, tile-strided); every CTA serves both images
     int occ = 0;
     CT_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hist_kernel, kThreads, smem));
     if (occ < 1) occ = 1;
     int64_t budget = ((int64_t)h->sm_count * occ) / B;
-    if (budget < 2) budget = 2;
-    for (int z = 0; z < 2; ++z) {
-        if (!imgs[z]) continue;
-        int64_t share = (int64_t)((double)budget * (double)npix[z] / (double)(npix[0] + npix[1]) + 0.5);
-        const int64_t want = (npix[z] / 2 + kThreads - 1) / kThreads;
-        if (share > want) share = want;
-        a.nblk[z] = (int)(share < 1 ? 1 : share);
-    }
+    const int64_t want = ((npix[0] > npix[1] ? npix[0] : npix[1]) / 2 + kThreads - 1) / kThreads;
+    if (budget > want) budget = want;
+    if (budget < 1) budget = 1;
+    const int nblk = (int)budget;
+    for (int z = 0; z < 2; ++z) a.nblk[z] = imgs[z] ? nblk : 0;
     a.rot = s->rot;
     a.rot_next = s->rot_next;
     a.rot_stride = s->rot_stride;
@@ -723,7 +747,7 @@ int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt
     CT_TRY(ensure_scratch(h, B));
     a.tickets = h->tickets;
     a.lut = lut_args(s, 0, trace, trace_iter, trace_niter);
-    hist_kernel<<<dim3(a.nblk[0] + a.nblk[1], B), kThreads, smem, h->stream>>>(a);
+    hist_kernel<<<dim3(nblk, B), kThreads, smem, h->stream>>>(a);
     h->launches++;
     CT_CUDA(h, cudaGetLastError());
     return CT_OK;

@@ -54,9 +54,11 @@ struct Pipe {
     unsigned char *stage;  // kStages * kTileBytes
     uint64_t *full;        // [kStages]
     uint64_t *empty;       // [kStages]
-    __device__ __forceinline__ explicit Pipe(void *base)
+    // `set` selects one of several barrier sets laid out after the stages, so that a kernel can run
+    // several pipelines one after the other over the same stage buffers (each starts at phase 0)
+    __device__ __forceinline__ explicit Pipe(void *base, int set = 0)
         : stage(static_cast<unsigned char *>(base)),
-          full(reinterpret_cast<uint64_t *>(static_cast<unsigned char *>(base) + kStages * kTileBytes)),
+          full(reinterpret_cast<uint64_t *>(static_cast<unsigned char *>(base) + kStages * kTileBytes) + 2 * kStages * set),
           empty(full + kStages) {}
     // one thread; followed by __syncthreads() in the caller
     __device__ __forceinline__ void init() {
