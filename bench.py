@@ -42,7 +42,7 @@ IDT_BYTES_PER_PIXEL_F32 = 24 + (24 + 36) + 3 * (36 + 48)
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=8, help="frame pairs per rank per step")
@@ -55,6 +55,19 @@ def parse_args():
     ap.add_argument("--kernels-only", action="store_true", help="profiling aid: only the timed device steps")
     ap.add_argument("--linear-only", action="store_true", help="profiling aid: only the linear-transfer extras")
     return ap.parse_args()
+
+
+def ncu_traffic_bytes_per_pixel(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per target pixel of `kernel`, from the committed
+    `ncu --set full` capture of this same command (profiles/r01_traffic.json, written by
+    tools/ncu_report.py); None if there is no capture for it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)["dram_bytes_per_pixel"]
+        vals = [v for k, vs in t.items() if k.startswith(kernel) for v in vs]
+        return sum(vals) / len(vals) if vals else None
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def measured_peaks():
@@ -337,9 +350,15 @@ def main():
         achieved.append(per_launch_bytes[dominant](it) * npix * F / (ms / 1e3) / 1e9)
     peak, peak_kind = measured_peaks()
     ach = sum(achieved) / len(achieved)
-    roofline = {"bound": "hbm", "kernel": {"hist": "hist_kernel", "remap": "remap_kernel", "ranges": "ranges_kernel"}[dominant],
+    kname = {"hist": "hist_kernel", "remap": "remap_kernel", "ranges": "ranges_kernel"}[dominant]
+    bpp = ncu_traffic_bytes_per_pixel(kname)
+    alg_bytes = sum(per_launch_bytes[dominant](int(n.split("_")[1]) if n.split("_")[1].isdigit() else 0) for n, _ in kern[dominant]) \
+        * npix * F / len(kern[dominant])
+    roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": ach, "peak": peak, "peak_source": peak_kind, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "traffic": None if bpp is None else bpp * npix * F,
+                "traffic_source": None if bpp is None else "profiles/r01_traffic.json: ncu dram bytes per pixel of the steady-state launches x pixels per launch",
                 "kernel_ms": {k: round(sum(t for _, t in v), 4) for k, v in kern.items()},
                 "step_algorithmic_GBps": IDT_BYTES_PER_PIXEL_F32 * npix * F / (ms_step / 1e3) / 1e9,
                 "step_frac": IDT_BYTES_PER_PIXEL_F32 * npix * F / (ms_step / 1e3) / 1e9 / peak}
