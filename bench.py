@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=8, help="frame pairs per rank per step")
-    ap.add_argument("--e2e-frames", type=int, default=4)
+    ap.add_argument("--e2e-frames", type=int, default=8)
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--width", type=int, default=W4K)
     ap.add_argument("--stress", action="store_true", help="i.i.d. uniform frames instead of the smooth field")

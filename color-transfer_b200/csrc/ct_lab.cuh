@@ -21,6 +21,26 @@
 namespace ct {
 namespace lab {
 
+// fp64 literals live in the constant bank: DMUL/DFMA take a c[bank][offset] operand directly,
+// whereas a 64-bit immediate costs two MOVs every time the compiler re-materialises it.
+struct LabConstants {
+    double m0[3], m1[3], m2[3];     // xyz_from_rgb rows / white
+    double r0[3], r1[3], r2[3];     // inv(xyz_from_rgb) columns * white
+    double inv1055, c0055, inv1292, thr_dec, thr_f, k7787, k16_116, third, four_thirds;
+    double c116, c500, c200, inv116, inv500, ninv200, thr_finv, inv7787, thr_enc, c1055, c1292;
+    double fifth, six_fifths, twelfth, thirteen_twelfths;
+};
+__constant__ LabConstants kL = {
+    {0.412453 / 0.95047, 0.357580 / 0.95047, 0.180423 / 0.95047},
+    {0.212671, 0.715160, 0.072169},
+    {0.019334 / 1.08883, 0.119193 / 1.08883, 0.950227 / 1.08883},
+    {3.079980302271805, -1.5371515162713183, -0.5428213080224701},
+    {-0.9212477523232383, 1.8759900014898907, 0.045247339514465995},
+    {0.05289046109881184, -0.20404133836651123, 1.1512320119619401},
+    1.0 / 1.055, 0.055, 1.0 / 12.92, 0.04045, 0.008856, 7.787, 16.0 / 116.0, 1.0 / 3.0, 4.0 / 3.0,
+    116.0, 500.0, 200.0, 1.0 / 116.0, 1.0 / 500.0, -1.0 / 200.0, 0.2068966, 1.0 / 7.787, 0.0031308, 1.055, 12.92,
+    0.2, 1.2, 1.0 / 12.0, 13.0 / 12.0};
+
 __device__ __forceinline__ float lg2_approx(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -59,33 +79,33 @@ __device__ __forceinline__ void rgb2lab_f32(const float (&rgb)[3], float (&out)[
 
 // ((v + 0.055) / 1.055)^2.4 for v > 0.04045, else v / 12.92
 __device__ __forceinline__ double srgb_decode(double v, float vf, float &rf) {
-    if (v > 0.04045) {
-        const double u = (v + 0.055) * (1.0 / 1.055);
+    if (v > kL.thr_dec) {
+        const double u = (v + kL.c0055) * kL.inv1055;
         const float uf = (vf + 0.055f) * (1.0f / 1.055f);
         const float y0 = ex2_approx(-0.2f * lg2_approx(uf));   // u^(-1/5)
         double y = (double)y0;
         const double y2 = y * y, y4 = y2 * y2;
-        y *= fma(-(u * y4) * y, 0.2, 1.2);                     // y (6 - u y^5) / 5
+        y *= fma(-(u * y4) * y, kL.fifth, kL.six_fifths);      // y (6 - u y^5) / 5
         const double uy = u * y;                               // u^(4/5)
         const float uyf = uf * y0;
         rf = uyf * uyf * uyf;
         return uy * uy * uy;
     }
     rf = vf * (1.0f / 12.92f);
-    return v * (1.0 / 12.92);
+    return v * kL.inv1292;
 }
 
 // cbrt(t) for t > 0.008856, else 7.787 t + 16/116
 __device__ __forceinline__ double lab_f(double t, float tf, float &rf) {
-    if (t > 0.008856) {
+    if (t > kL.thr_f) {
         const float y0 = ex2_approx(-0.33333334f * lg2_approx(tf));  // t^(-1/3)
         double y = (double)y0;
-        y *= fma(-(t * y) * (y * y), 1.0 / 3.0, 4.0 / 3.0);          // y (4 - t y^3) / 3
+        y *= fma(-(t * y) * (y * y), kL.third, kL.four_thirds);      // y (4 - t y^3) / 3
         rf = tf * (y0 * y0);
         return t * (y * y);
     }
     rf = fmaf(7.787f, tf, 16.0f / 116.0f);
-    return fma(7.787, t, 16.0 / 116.0);
+    return fma(kL.k7787, t, kL.k16_116);
 }
 
 __device__ __forceinline__ void rgb2lab(const double (&rgb)[3], const float (&rgbf)[3], double (&out)[3], float (&outf)[3]) {
@@ -94,12 +114,12 @@ __device__ __forceinline__ void rgb2lab(const double (&rgb)[3], const float (&rg
 #pragma unroll
     for (int c = 0; c < 3; ++c) l[c] = srgb_decode(rgb[c], rgbf[c], lf[c]);
     float fxf, fyf, fzf;
-    const double fx = lab_f(CT_XYZ_ROW0(double, l[0], l[1], l[2]), CT_XYZ_ROW0(float, lf[0], lf[1], lf[2]), fxf);
-    const double fy = lab_f(CT_XYZ_ROW1(double, l[0], l[1], l[2]), CT_XYZ_ROW1(float, lf[0], lf[1], lf[2]), fyf);
-    const double fz = lab_f(CT_XYZ_ROW2(double, l[0], l[1], l[2]), CT_XYZ_ROW2(float, lf[0], lf[1], lf[2]), fzf);
-    out[0] = fma(116.0, fy, -16.0);
-    out[1] = 500.0 * (fx - fy);
-    out[2] = 200.0 * (fy - fz);
+    const double fx = lab_f(fma(kL.m0[2], l[2], fma(kL.m0[1], l[1], kL.m0[0] * l[0])), CT_XYZ_ROW0(float, lf[0], lf[1], lf[2]), fxf);
+    const double fy = lab_f(fma(kL.m1[2], l[2], fma(kL.m1[1], l[1], kL.m1[0] * l[0])), CT_XYZ_ROW1(float, lf[0], lf[1], lf[2]), fyf);
+    const double fz = lab_f(fma(kL.m2[2], l[2], fma(kL.m2[1], l[1], kL.m2[0] * l[0])), CT_XYZ_ROW2(float, lf[0], lf[1], lf[2]), fzf);
+    out[0] = fma(kL.c116, fy, -16.0);
+    out[1] = kL.c500 * (fx - fy);
+    out[2] = kL.c200 * (fy - fz);
     outf[0] = fmaf(116.0f, fyf, -16.0f);
     outf[1] = 500.0f * (fxf - fyf);
     outf[2] = 200.0f * (fyf - fzf);
@@ -113,7 +133,7 @@ __device__ __forceinline__ void rgb2lab(const double (&rgb)[3], const float (&rg
                 : (T)0.05289046109881184 * (X) + (T)-0.20404133836651123 * (Y) + (T)1.1512320119619401 * (Z))
 
 __device__ __forceinline__ double finv(double f) {
-    return f > 0.2068966 ? f * f * f : (f - 16.0 / 116.0) * (1.0 / 7.787);
+    return f > kL.thr_finv ? f * f * f : (f - kL.k16_116) * kL.inv7787;
 }
 __device__ __forceinline__ float finv_f(float f) {
     return f > 0.2068966f ? f * f * f : (f - 16.0f / 116.0f) * (1.0f / 7.787f);
@@ -122,34 +142,35 @@ __device__ __forceinline__ float finv_f(float f) {
 // 1.055 c^(1/2.4) - 0.055 for c > 0.0031308, else 12.92 c; then np.clip(., 0, 1)
 __device__ __forceinline__ double srgb_encode(double c, float cf) {
     double s;
-    if (c > 0.0031308) {
+    if (c > kL.thr_enc) {
         const float y0 = ex2_approx(-0.083333336f * lg2_approx(cf));  // c^(-1/12)
         double y = (double)y0;
         double y2 = y * y, y4 = y2 * y2;
         const double y12 = (y4 * y4) * y4;
-        y *= fma(-c * y12, 1.0 / 12.0, 13.0 / 12.0);                   // y (13 - c y^12) / 12
+        y *= fma(-c * y12, kL.twelfth, kL.thirteen_twelfths);           // y (13 - c y^12) / 12
         y2 = y * y;
         y4 = y2 * y2;
-        s = fma(1.055, c * ((y4 * y2) * y), -0.055);                    // c y^7 = c^(5/12)
+        s = fma(kL.c1055, c * ((y4 * y2) * y), -kL.c0055);              // c y^7 = c^(5/12)
     } else {
-        s = 12.92 * c;
+        s = kL.c1292 * c;
     }
     s = s < 0.0 ? 0.0 : s;  // NaN stays NaN, like np.clip
     return s > 1.0 ? 1.0 : s;
 }
 
 __device__ __forceinline__ void lab2rgb(const double (&labv)[3], const float (&labf)[3], double (&rgb)[3]) {
-    const double fy = (labv[0] + 16.0) * (1.0 / 116.0);
-    const double fx = fma(labv[1], 1.0 / 500.0, fy);
-    double fz = fma(labv[2], -1.0 / 200.0, fy);
+    const double fy = (labv[0] + 16.0) * kL.inv116;
+    const double fx = fma(labv[1], kL.inv500, fy);
+    double fz = fma(labv[2], kL.ninv200, fy);
     fz = fz < 0.0 ? 0.0 : fz;  // skimage zeroes invalid z (and warns)
     const float fyf = (labf[0] + 16.0f) * (1.0f / 116.0f);
     const float fxf = fmaf(labf[1], 1.0f / 500.0f, fyf);
     const float fzf = fmaxf(fmaf(labf[2], -1.0f / 200.0f, fyf), 0.0f);
     const double X = finv(fx), Y = finv(fy), Z = finv(fz);
     const float Xf = finv_f(fxf), Yf = finv_f(fyf), Zf = finv_f(fzf);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) rgb[c] = srgb_encode(CT_RGB_ROW(double, c, X, Y, Z), CT_RGB_ROW(float, c, Xf, Yf, Zf));
+    rgb[0] = srgb_encode(fma(kL.r0[2], Z, fma(kL.r0[1], Y, kL.r0[0] * X)), CT_RGB_ROW(float, 0, Xf, Yf, Zf));
+    rgb[1] = srgb_encode(fma(kL.r1[2], Z, fma(kL.r1[1], Y, kL.r1[0] * X)), CT_RGB_ROW(float, 1, Xf, Yf, Zf));
+    rgb[2] = srgb_encode(fma(kL.r2[2], Z, fma(kL.r2[1], Y, kL.r2[0] * X)), CT_RGB_ROW(float, 2, Xf, Yf, Zf));
 }
 
 }  // namespace lab
