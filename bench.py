@@ -54,6 +54,10 @@ def parse_args():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--kernels-only", action="store_true", help="profiling aid: only the timed device steps")
     ap.add_argument("--linear-only", action="store_true", help="profiling aid: only the linear-transfer extras")
+    ap.add_argument("--workload", default="video4k", choices=["video4k", "rowshard"],
+                    help="video4k: configs[3] (default, the bench line); rowshard: configs[4], one 16384x16384 pair "
+                         "split by rows over the ranks with NCCL all-reduces of range keys / counts / moments")
+    ap.add_argument("--side", type=int, default=16384, help="rowshard: side of the square pair")
     return ap.parse_args()
 
 
@@ -278,6 +282,11 @@ def main():
     if a.linear_only:
         print(json.dumps(linear_extras(torch, device, synth, _cabi, handle, dev, measured_peaks()[0])))
         return
+    if a.workload == "rowshard":
+        run_rowshard(a, torch, dist, device, synth, _cabi, handle, dev, world, rank, barrier, max_over_ranks)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # frames k = rank, rank + world, ...: rotations pre-drawn in frame order after seed 42
     np.random.seed(42)
@@ -409,6 +418,60 @@ def main():
         dist.destroy_process_group()
 
 
+def run_rowshard(a, torch, dist, device, synth, _cabi, handle, dev, world, rank, barrier, max_over_ranks):
+    """configs[4]: one side x side float32 pair, contiguous row blocks per rank (strong scaling).
+    IDT: 1 + n_iter MIN all-reduces of 6 int64 keys, n_iter SUM all-reduces of 6*bins int64 counts;
+    MKL / Reinhard: one all-gather of 2x10 raw moments.  Device-resident shards, CUDA events,
+    max over ranks."""
+    import numpy as np
+    from color_transfer_b200 import sharded
+    side = a.side
+    r0, r1 = sharded.row_partition(side, world, rank)
+    rows = r1 - r0
+    # every rank generates only its rows (seeded per row block so the pair is the same for any world size)
+    tgt, ref = synth.frame_pairs_cuda(1, rows, side, 3000 + r0, dev)
+    tgt, ref = tgt[0], ref[0]
+    np.random.seed(42)
+    rot = sharded.predraw_rotations(1, N_ITER)[0]
+    comm = sharded.Comm()
+    results = {}
+    peak, _ = measured_peaks()
+    npix = side * side
+
+    def timed(fn, reps):
+        for _ in range(2):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / reps
+
+    backend = sharded.CudaIdtBackend(tgt, ref, rot, BINS, N_ITER, handle)
+
+    def idt():
+        def between(name, tensor):
+            comm.min_(tensor) if name == "keys" else comm.sum_(tensor)
+        backend.run(between)
+
+    ms = timed(idt, max(2, min(a.steps, 5)))
+    results["idt"] = {"ms_per_pair": ms, "Mpix/s": npix / 1e6 / (ms / 1e3),
+                      "frac_of_hbm_aggregate": IDT_BYTES_PER_PIXEL_F32 * npix / (ms / 1e3) / 1e9 / (peak * world),
+                      "collectives_per_pair": 1 + 2 * N_ITER - 1 + 1}
+    for name, code, bpp in (("mkl", _cabi.CT_MKL_MK, 60), ("reinhard", _cabi.CT_REINHARD, 48)):
+        ms = timed(lambda: sharded.linear_transfer_sharded(code, tgt, ref, comm=comm, handle=handle), max(2, min(a.steps, 5)))
+        results[name] = {"ms_per_pair": ms, "Mpix/s": npix / 1e6 / (ms / 1e3),
+                         "frac_of_hbm_aggregate": bpp * npix / (ms / 1e3) / 1e9 / (peak * world), "collectives_per_pair": 1}
+    if rank == 0:
+        print(json.dumps({"metric": "stereopair Mpix/s (one %dx%d pair, row-sharded)" % (side, side), "unit": "Mpix/s",
+                          "n_gpus": world, "scaling": "strong", "value": results["idt"]["Mpix/s"], "data": "synthetic",
+                          "config": {"workload": "configs[4]: single %dx%d float32 stereopair row-sharded with NCCL all-reduces" % (side, side),
+                                     "rows_per_rank": rows, "bins": BINS, "n_iter": N_ITER}, "results": results}))
+
+
 def linear_extras(torch, device, synth, _cabi, handle, dev, peak):
     """Secondary numbers for the linear transfers (configs[2] shape: 960x540 float32 pairs)."""
     out = {}
@@ -431,6 +494,29 @@ def linear_extras(torch, device, synth, _cabi, handle, dev, peak):
         out[name] = {"Mpix/s": B * H * W / 1e6 / (ms / 1e3), "ms_per_batch": ms, "pairs": B, "shape": [H, W, 3],
                      "algorithmic_GBps": gbps, "frac_of_hbm": gbps / peak,
                      "note": "batch working set 1.2-2.0 GB, larger than L2"}
+    # configs[0] / configs[1] shape: one 1080x860 float64 pair (L2-resident, launch-latency regime)
+    import numpy as np
+    from color_transfer_b200 import batch
+    t64, r64 = synth.frame_pairs_cuda(1, 860, 1080, 964, dev, dtype=torch.float64)
+    np.random.seed(42)
+    rot = torch.from_numpy(batch.draw_rotations(N_ITER)[None]).to(dev)
+    single = {"reinhard": lambda: device.linear_transfer(_cabi.CT_REINHARD, t64, r64, handle=handle),
+              "mkl": lambda: device.linear_transfer(_cabi.CT_MKL_MK, t64, r64, handle=handle),
+              "idt": lambda: device.idt_transfer(t64, r64, rot, BINS, N_ITER, handle=handle)}
+    lat = {}
+    for name, fn in single.items():
+        for _ in range(5):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(50):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 50 * 1e3
+        lat[name] = {"us_per_pair": us, "Mpix/s": 860 * 1080 / us}
+    out["single_pair_1080x860_f64"] = dict(lat, note="device-resident, back-to-back calls, working set fits L2")
     return out
 
 
