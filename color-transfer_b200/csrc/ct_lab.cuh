@@ -4,13 +4,11 @@
 // The three fractional powers (x^2.4, cbrt, x^(1/2.4)) are the cost of this path, and on B200
 // the scarce unit is the XU pipe (MUFU and every F2F/I2F conversion: 16 lanes/clk/SM, a quarter
 // of the fp64 rate).  Each power is therefore computed as
-//     seed   y0 ~ x^(-1/n) from MUFU lg2/ex2 on an fp32 "shadow" of the operand  (2 XU ops)
+//     seed   y0 ~ x^(-1/n) from MUFU lg2/ex2 on the operand rounded to fp32             (2-3 XU ops)
 //     polish one DIVISION-FREE Newton step for y = x^(-1/n) in fp64:
 //            y = y0 * ((n+1) - x*y0^n) / n          error (n+1)/2 * e0^2 ~ 1e-12  (1 XU op: y0 -> double)
 //     result x^2.4 = (x*y)^3 (n=5),  cbrt x = x*y^2 (n=3),  x^(5/12) = x*y^7 (n=12)
-// i.e. 3 XU operations per power instead of 7 (pow() would be ~150 fp64 instructions).  The
-// shadow chain (the same formulas in fp32, only ever used to seed) keeps every intermediate
-// available as a float without converting doubles back.
+// i.e. 3-4 XU operations per power instead of 7 (pow() would be ~150 fp64 instructions).
 //
 // The statistics pass (mean / std over millions of pixels) uses the fp32 chain alone: its
 // per-pixel error (~3e-7 relative) shifts the Lab means by ~1e-5 of a Lab unit, 1e-7 in RGB.
@@ -74,77 +72,55 @@ __device__ __forceinline__ void rgb2lab_f32(const float (&rgb)[3], float (&out)[
     out[2] = 200.0f * (fy - fz);
 }
 
-// ------------------------------------------------------------------ fp64 chain with fp32 shadow
-// Every function takes the operand as (double x, float xf ~ x) and returns (double r, float rf ~ r).
+// ------------------------------------------------------------------ fp64 chain, fp32 seeds
+// The seed of each power needs its operand as a float: one F2F (XU) per power, except for the
+// gamma decode of float32 images whose operand already is one (`vf`).
 
 // ((v + 0.055) / 1.055)^2.4 for v > 0.04045, else v / 12.92
-__device__ __forceinline__ double srgb_decode(double v, float vf, float &rf) {
+__device__ __forceinline__ double srgb_decode(double v, float vf) {
     if (v > kL.thr_dec) {
         const double u = (v + kL.c0055) * kL.inv1055;
         const float uf = (vf + 0.055f) * (1.0f / 1.055f);
-        const float y0 = ex2_approx(-0.2f * lg2_approx(uf));   // u^(-1/5)
-        double y = (double)y0;
+        double y = (double)ex2_approx(-0.2f * lg2_approx(uf));   // u^(-1/5)
         const double y2 = y * y, y4 = y2 * y2;
-        y *= fma(-(u * y4) * y, kL.fifth, kL.six_fifths);      // y (6 - u y^5) / 5
-        const double uy = u * y;                               // u^(4/5)
-        const float uyf = uf * y0;
-        rf = uyf * uyf * uyf;
+        y *= fma(-(u * y4) * y, kL.fifth, kL.six_fifths);        // y (6 - u y^5) / 5
+        const double uy = u * y;                                 // u^(4/5)
         return uy * uy * uy;
     }
-    rf = vf * (1.0f / 12.92f);
     return v * kL.inv1292;
 }
 
 // cbrt(t) for t > 0.008856, else 7.787 t + 16/116
-__device__ __forceinline__ double lab_f(double t, float tf, float &rf) {
+__device__ __forceinline__ double lab_f(double t) {
     if (t > kL.thr_f) {
-        const float y0 = ex2_approx(-0.33333334f * lg2_approx(tf));  // t^(-1/3)
-        double y = (double)y0;
-        y *= fma(-(t * y) * (y * y), kL.third, kL.four_thirds);      // y (4 - t y^3) / 3
-        rf = tf * (y0 * y0);
+        double y = (double)ex2_approx(-0.33333334f * lg2_approx((float)t));  // t^(-1/3)
+        y *= fma(-(t * y) * (y * y), kL.third, kL.four_thirds);               // y (4 - t y^3) / 3
         return t * (y * y);
     }
-    rf = fmaf(7.787f, tf, 16.0f / 116.0f);
     return fma(kL.k7787, t, kL.k16_116);
 }
 
-__device__ __forceinline__ void rgb2lab(const double (&rgb)[3], const float (&rgbf)[3], double (&out)[3], float (&outf)[3]) {
-    float lf[3];
+__device__ __forceinline__ void rgb2lab(const double (&rgb)[3], const float (&rgbf)[3], double (&out)[3]) {
     double l[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) l[c] = srgb_decode(rgb[c], rgbf[c], lf[c]);
-    float fxf, fyf, fzf;
-    const double fx = lab_f(fma(kL.m0[2], l[2], fma(kL.m0[1], l[1], kL.m0[0] * l[0])), CT_XYZ_ROW0(float, lf[0], lf[1], lf[2]), fxf);
-    const double fy = lab_f(fma(kL.m1[2], l[2], fma(kL.m1[1], l[1], kL.m1[0] * l[0])), CT_XYZ_ROW1(float, lf[0], lf[1], lf[2]), fyf);
-    const double fz = lab_f(fma(kL.m2[2], l[2], fma(kL.m2[1], l[1], kL.m2[0] * l[0])), CT_XYZ_ROW2(float, lf[0], lf[1], lf[2]), fzf);
+    for (int c = 0; c < 3; ++c) l[c] = srgb_decode(rgb[c], rgbf[c]);
+    const double fx = lab_f(fma(kL.m0[2], l[2], fma(kL.m0[1], l[1], kL.m0[0] * l[0])));
+    const double fy = lab_f(fma(kL.m1[2], l[2], fma(kL.m1[1], l[1], kL.m1[0] * l[0])));
+    const double fz = lab_f(fma(kL.m2[2], l[2], fma(kL.m2[1], l[1], kL.m2[0] * l[0])));
     out[0] = fma(kL.c116, fy, -16.0);
     out[1] = kL.c500 * (fx - fy);
     out[2] = kL.c200 * (fy - fz);
-    outf[0] = fmaf(116.0f, fyf, -16.0f);
-    outf[1] = 500.0f * (fxf - fyf);
-    outf[2] = 200.0f * (fyf - fzf);
 }
-
-// scipy.linalg.inv(xyz_from_rgb) (what skimage computes at import), columns pre-multiplied by
-// the D65 white so that rgb = m @ (finv(fx), finv(fy), finv(fz)).
-#define CT_RGB_ROW(T, c, X, Y, Z)                                                                       \
-    ((c) == 0 ? (T)3.079980302271805 * (X) + (T)-1.5371515162713183 * (Y) + (T)-0.5428213080224701 * (Z) \
-     : (c) == 1 ? (T)-0.9212477523232383 * (X) + (T)1.8759900014898907 * (Y) + (T)0.045247339514465995 * (Z) \
-                : (T)0.05289046109881184 * (X) + (T)-0.20404133836651123 * (Y) + (T)1.1512320119619401 * (Z))
 
 __device__ __forceinline__ double finv(double f) {
     return f > kL.thr_finv ? f * f * f : (f - kL.k16_116) * kL.inv7787;
 }
-__device__ __forceinline__ float finv_f(float f) {
-    return f > 0.2068966f ? f * f * f : (f - 16.0f / 116.0f) * (1.0f / 7.787f);
-}
 
 // 1.055 c^(1/2.4) - 0.055 for c > 0.0031308, else 12.92 c; then np.clip(., 0, 1)
-__device__ __forceinline__ double srgb_encode(double c, float cf) {
+__device__ __forceinline__ double srgb_encode(double c) {
     double s;
     if (c > kL.thr_enc) {
-        const float y0 = ex2_approx(-0.083333336f * lg2_approx(cf));  // c^(-1/12)
-        double y = (double)y0;
+        double y = (double)ex2_approx(-0.083333336f * lg2_approx((float)c));  // c^(-1/12)
         double y2 = y * y, y4 = y2 * y2;
         const double y12 = (y4 * y4) * y4;
         y *= fma(-c * y12, kL.twelfth, kL.thirteen_twelfths);           // y (13 - c y^12) / 12
@@ -158,19 +134,15 @@ __device__ __forceinline__ double srgb_encode(double c, float cf) {
     return s > 1.0 ? 1.0 : s;
 }
 
-__device__ __forceinline__ void lab2rgb(const double (&labv)[3], const float (&labf)[3], double (&rgb)[3]) {
+__device__ __forceinline__ void lab2rgb(const double (&labv)[3], double (&rgb)[3]) {
     const double fy = (labv[0] + 16.0) * kL.inv116;
     const double fx = fma(labv[1], kL.inv500, fy);
     double fz = fma(labv[2], kL.ninv200, fy);
     fz = fz < 0.0 ? 0.0 : fz;  // skimage zeroes invalid z (and warns)
-    const float fyf = (labf[0] + 16.0f) * (1.0f / 116.0f);
-    const float fxf = fmaf(labf[1], 1.0f / 500.0f, fyf);
-    const float fzf = fmaxf(fmaf(labf[2], -1.0f / 200.0f, fyf), 0.0f);
     const double X = finv(fx), Y = finv(fy), Z = finv(fz);
-    const float Xf = finv_f(fxf), Yf = finv_f(fyf), Zf = finv_f(fzf);
-    rgb[0] = srgb_encode(fma(kL.r0[2], Z, fma(kL.r0[1], Y, kL.r0[0] * X)), CT_RGB_ROW(float, 0, Xf, Yf, Zf));
-    rgb[1] = srgb_encode(fma(kL.r1[2], Z, fma(kL.r1[1], Y, kL.r1[0] * X)), CT_RGB_ROW(float, 1, Xf, Yf, Zf));
-    rgb[2] = srgb_encode(fma(kL.r2[2], Z, fma(kL.r2[1], Y, kL.r2[0] * X)), CT_RGB_ROW(float, 2, Xf, Yf, Zf));
+    rgb[0] = srgb_encode(fma(kL.r0[2], Z, fma(kL.r0[1], Y, kL.r0[0] * X)));
+    rgb[1] = srgb_encode(fma(kL.r1[2], Z, fma(kL.r1[1], Y, kL.r1[0] * X)));
+    rgb[2] = srgb_encode(fma(kL.r2[2], Z, fma(kL.r2[1], Y, kL.r2[0] * X)));
 }
 
 }  // namespace lab

@@ -79,7 +79,7 @@ __device__ __forceinline__ void moments_image(const Img &im, int64_t pair, doubl
     }
 }
 
-__global__ void __launch_bounds__(kThreads) moments_kernel(MomentsArgs a) {
+__global__ void __launch_bounds__(kThreads, 3) moments_kernel(MomentsArgs a) {
     const int z = blockIdx.z;
     const int64_t pair = blockIdx.y;
     double acc[9];
@@ -176,18 +176,14 @@ struct ApplyArgs {
 template <bool LAB>
 __device__ __forceinline__ void apply_pixel(const double *xf, const float *xff, const double (&x)[3],
                                             const float (&xs)[3], double (&y)[3]) {
-    if (LAB) {  // xs / xff: fp32 shadows of the pixel and the transform, seeds only
+    if (LAB) {  // xs: the pixel as floats (seeds of the gamma decode)
         double l[3], m[3];
-        float lf[3], mf[3];
-        lab::rgb2lab(x, xs, l, lf);
+        lab::rgb2lab(x, xs, l);
         // (lab - mean_t) * std_r / std_t + mean_r   (linear.py:38)
         m[0] = fma(l[0] - xf[9], xf[0], xf[12]);
         m[1] = fma(l[1] - xf[10], xf[4], xf[13]);
         m[2] = fma(l[2] - xf[11], xf[8], xf[14]);
-        mf[0] = fmaf(lf[0] - xff[9], xff[0], xff[12]);
-        mf[1] = fmaf(lf[1] - xff[10], xff[4], xff[13]);
-        mf[2] = fmaf(lf[2] - xff[11], xff[8], xff[14]);
-        lab::lab2rgb(m, mf, y);
+        lab::lab2rgb(m, y);
     } else {
         const double d0 = x[0] - xf[9], d1 = x[1] - xf[10], d2 = x[2] - xf[11];
 #pragma unroll
@@ -196,7 +192,7 @@ __device__ __forceinline__ void apply_pixel(const double *xf, const float *xff, 
 }
 
 template <typename SIO, typename DIO, bool VEC, bool LAB>
-__global__ void __launch_bounds__(kThreads) apply_kernel(ApplyArgs a) {
+__global__ void __launch_bounds__(kThreads, LAB ? 4 : 3) apply_kernel(ApplyArgs a) {
     using TS = typename SIO::elem_t;
     using TD = typename DIO::elem_t;
     const int64_t pair = blockIdx.y;

@@ -1,5 +1,5 @@
-for lib in default v1 v2; do
+for lib in default a34m2 a33m3 a34m3 a44m4; do
   if [ "$lib" = default ]; then unset CT_B200_LIB; else export CT_B200_LIB=$PWD/tools/scratch/libct_$lib.so; fi
-  python bench.py --no-cpu-baseline --no-extras --steps 5 --e2e-frames 1 2>/dev/null | python -c "
-import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$lib', round(d['value']), d['roofline']['kernel_ms'])"
+  python bench.py --linear-only 2>/dev/null | python -c "
+import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$lib', {k:(round(v['Mpix/s']), round(v['frac_of_hbm'],3)) for k,v in d.items() if 'Mpix/s' in v})"
 done
