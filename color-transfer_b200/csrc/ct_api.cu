@@ -15,6 +15,7 @@ int check_batch(ct_context *h, const ct_batch *b, const char *name) {
     if (b->dtype != CT_F32 && b->dtype != CT_F64) return fail(h, CT_E_INVALID, "%s.dtype unknown", name);
     if (b->layout != CT_HWC && b->layout != CT_CHW) return fail(h, CT_E_INVALID, "%s.layout unknown", name);
     if (b->count > 65535) return fail(h, CT_E_UNSUPPORTED, "%s.count above 65535 pairs per call", name);
+    if (b->npix >= ((int64_t)1 << 31)) return fail(h, CT_E_UNSUPPORTED, "%s.npix must be below 2^31 pixels per image", name);
     if (((uintptr_t)b->data) % elem_size(b->dtype)) return fail(h, CT_E_INVALID, "%s.data is not element aligned", name);
     return CT_OK;
 }

@@ -82,3 +82,17 @@ def iterative_distribution_transfer(target, reference, bins=255, n_iter=4, *, ro
     h.check(rc)
     del t_keep, r_keep
     return out
+
+
+def _idt_device_impl(target, reference, bins=255, n_iter=4):
+    """[B,H,W,3] CUDA tensors -> [B,H,W,3] float64 CUDA tensor.  Rotations are drawn pair by pair
+    from the global numpy RNG, n_iter per pair - the order a loop over the reference function sees."""
+    import torch
+
+    from .. import device
+    b = target.shape[0]
+    rot = np.stack([draw_rotations(n_iter) for _ in range(b)])
+    return device.idt_transfer(target, reference, torch.from_numpy(rot).to(target.device), bins, n_iter)
+
+
+iterative_distribution_transfer.device_impl = _idt_device_impl

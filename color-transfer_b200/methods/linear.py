@@ -75,3 +75,16 @@ def monge_kantorovitch_color_transfer(target, reference, decomposition="MK", *, 
     if decomposition not in _DECOMPOSITIONS:
         raise ValueError("Unknown decomposition, use either 'cholesky', 'sqrt', or 'MK'")
     return _run(_DECOMPOSITIONS[decomposition], target, reference, np.float64, out, handle)
+
+
+def _device_impl(method):
+    def run(target, reference):
+        """[B,H,W,3] CUDA tensors -> [B,H,W,3] CUDA tensor; same kernels, no host round trip."""
+        from .. import device
+        return device.linear_transfer(method, target, reference)
+    return run
+
+
+color_transfer_between_images.device_impl = _device_impl(_cabi.CT_REINHARD)
+color_transfer_in_correlated_color_space.device_impl = _device_impl(_cabi.CT_CCS)
+monge_kantorovitch_color_transfer.device_impl = _device_impl(_cabi.CT_MKL_MK)

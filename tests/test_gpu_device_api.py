@@ -105,3 +105,34 @@ def test_two_gpu_row_sharding_and_frame_parallel(mods):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "DIST_GPU_CHECK_OK" in res.stdout
+
+
+def test_runner_contract_host_and_device_paths(mods):
+    """methods.Runner(func_spec).forward(batch): the reference's CHW float32 contract (ref:
+    methods/__init__.py:18-27) through the numpy path, and the device-resident fast path."""
+    torch, _cabi, batch, device, sharded, synth, oracle = mods
+    import methods
+    t, r = _stack(3, 40, 56, np.float32, seed=300)
+    bt = {"target": torch.from_numpy(np.ascontiguousarray(t.transpose(0, 3, 1, 2))),
+          "reference": torch.from_numpy(np.ascontiguousarray(r.transpose(0, 3, 1, 2)))}
+    for spec, fn in (("methods.linear.color_transfer_between_images", oracle.color_transfer_between_images),
+                     ("methods.linear.monge_kantorovitch_color_transfer", oracle.monge_kantorovitch_color_transfer)):
+        runner = methods.Runner(spec)
+        host = runner(bt)
+        assert host.shape == (3, 3, 40, 56) and host.dtype == torch.float32
+        dev = runner({k: v.cuda() for k, v in bt.items()})
+        assert dev.is_cuda and dev.dtype == torch.float32
+        assert torch.equal(dev.cpu(), host)
+        for i in range(3):
+            want = fn(t[i].astype(np.float64), r[i].astype(np.float64))
+            assert np.max(np.abs(host[i].permute(1, 2, 0).numpy() - want)) < 1e-4
+    runner = methods.Runner("methods.iterative.iterative_distribution_transfer")
+    np.random.seed(11)
+    host = runner(bt)
+    np.random.seed(11)
+    dev = runner({k: v.cuda() for k, v in bt.items()})
+    assert torch.equal(dev.cpu(), host)          # same rotations, same kernels
+    np.random.seed(11)
+    for i in range(3):
+        want = oracle.iterative_distribution_transfer(t[i], r[i])
+        assert np.max(np.abs(host[i].permute(1, 2, 0).numpy() - want)) < 1e-6
