@@ -517,7 +517,43 @@ def linear_extras(torch, device, synth, _cabi, handle, dev, peak):
         us = e0.elapsed_time(e1) / 50 * 1e3
         lat[name] = {"us_per_pair": us, "Mpix/s": 860 * 1080 / us}
     out["single_pair_1080x860_f64"] = dict(lat, note="device-resident, back-to-back calls, working set fits L2")
+    out["dropin_pair0964"] = dropin_pair0964()
     return out
+
+
+def dropin_pair0964():
+    """configs[0] / configs[1]: the reference's own stereo pair through the reference-facing numpy
+    functions (pageable float64 arrays in, new array out, H2D/D2H inside the call), wall clock per
+    call, next to the CPU oracle on the same arrays."""
+    import numpy as np
+    try:
+        from PIL import Image
+        left = np.asarray(Image.open(os.path.join(ROOT, "tests", "golden", "0964_L.png")).convert("RGB")) / 255.0
+        right = np.asarray(Image.open(os.path.join(ROOT, "tests", "golden", "0964_R.png")).convert("RGB")) / 255.0
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)}
+    import methods.iterative
+    import methods.linear
+    from oracle import reference_numpy as oracle
+    res = {"shape": list(left.shape), "dtype": "float64"}
+    cases = (("color_transfer_between_images", methods.linear.color_transfer_between_images, oracle.color_transfer_between_images),
+             ("monge_kantorovitch_color_transfer", methods.linear.monge_kantorovitch_color_transfer, oracle.monge_kantorovitch_color_transfer),
+             ("iterative_distribution_transfer", methods.iterative.iterative_distribution_transfer, oracle.iterative_distribution_transfer))
+    for name, ours, ref in cases:
+        np.random.seed(42)
+        ours(left, right)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            np.random.seed(42)
+            got = ours(left, right)
+        t_ours = (time.perf_counter() - t0) / 5
+        np.random.seed(42)
+        t0 = time.perf_counter()
+        want = ref(left, right)
+        t_ref = time.perf_counter() - t0
+        res[name] = {"ms_per_call": t_ours * 1e3, "cpu_oracle_ms": t_ref * 1e3, "speedup": t_ref / t_ours,
+                     "max_abs_diff": float(np.max(np.abs(got - want)))}
+    return res
 
 
 if __name__ == "__main__":
