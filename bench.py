@@ -395,6 +395,25 @@ def main():
     # the device-resident result and the host-API result must agree (same kernels)
     same = bool(np.array_equal(ho[0], out[0].cpu().numpy()))
 
+    # ---- the same frames as uint8 video frames: 3 B/px over PCIe each way
+    h8t = batch.pinned_empty((Fe, H, W, 3), np.uint8)
+    h8r = batch.pinned_empty((Fe, H, W, 3), np.uint8)
+    h8o = batch.pinned_empty((Fe, H, W, 3), np.uint8)
+    h8t[...] = np.rint(ht * 255).astype(np.uint8)
+    h8r[...] = np.rint(hr * 255).astype(np.uint8)
+    batch.idt_frames_u8(h8t, h8r, BINS, N_ITER, rotations=rot_e2e, out=h8o, handle=handle)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        batch.idt_frames_u8(h8t, h8r, BINS, N_ITER, rotations=rot_e2e, out=h8o, handle=handle)
+    barrier()
+    u8_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    want8 = np.rint(np.clip(ho[0], 0, 1) * 255).astype(np.uint8)
+    e2e_u8 = {"value": world * Fe * npix / 1e6 / u8_s, "unit": "Mpix/s", "h2d_bytes_per_step": int(2 * Fe * npix * 3),
+              "d2h_bytes_per_step": int(Fe * npix * 3), "frames_per_step": Fe, "ms_per_step": u8_s * 1e3,
+              "api": "color_transfer_b200.batch.idt_frames_u8 -> ct_idt_transfer_host_u8 (uint8 frames in and out)",
+              "matches_float_path_bytes": float(np.mean(h8o[0] == want8))}
+
     extras = {}
     if not a.no_extras and rank == 0:
         extras = linear_extras(torch, device, synth, _cabi, handle, dev, peak)
@@ -411,7 +430,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, F),
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "host_api_matches_device_api": same, "extras": extras}
         print(json.dumps(line))
     if world > 1:

@@ -64,6 +64,10 @@ SIGNATURES = {
     "ct_linear_apply": (ctypes.c_int, [_P, ctypes.c_int, _BP, _P, _BP]),
     "ct_linear_transfer": (ctypes.c_int, [_P, ctypes.c_int, _BP, _BP, _BP, _P, _P]),
     "ct_linear_transfer_host": (ctypes.c_int, [_P, ctypes.c_int, _BP, _BP, _BP]),
+    "ct_linear_transfer_host_u8": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, _P, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
+                                                  ctypes.c_int32]),
+    "ct_idt_transfer_host_u8": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
+                                               _P, ctypes.c_int32, ctypes.c_int32]),
     "ct_idt_key_of": (ctypes.c_int64, [ctypes.c_double]),
     "ct_idt_value_of": (ctypes.c_double, [ctypes.c_int64]),
     "ct_idt_keys_init": (ctypes.c_int, [_P, _P, ctypes.c_int64]),

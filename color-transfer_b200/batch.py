@@ -22,10 +22,60 @@ _METHODS = {"reinhard": _cabi.CT_REINHARD, "ccs": _cabi.CT_CCS, "mkl": _cabi.CT_
 def pinned_empty(shape, dtype):
     """A numpy array backed by page-locked memory (allocated through torch)."""
     import torch
-    t = torch.empty(tuple(shape), dtype={np.dtype(np.float32): torch.float32,
-                                         np.dtype(np.float64): torch.float64}[np.dtype(dtype)]).pin_memory()
+    t = torch.empty(tuple(shape), dtype={np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+                                         np.dtype(np.uint8): torch.uint8}[np.dtype(dtype)]).pin_memory()
     a = t.numpy()
     return a
+
+
+def _stack_u8(x, name):
+    a = np.asarray(x)
+    if a.ndim != 4 or a.shape[-1] != 3 or a.dtype != np.uint8:
+        raise ValueError(f"{name} must be a uint8 array of shape [B, H, W, 3]")
+    return np.ascontiguousarray(a)
+
+
+def linear_transfer_frames_u8(method, targets, references, out=None, as_float32=True, handle=None):
+    """uint8 frames in, uint8 frames out: decode k/255 (float32 like the reference's dataset loader,
+    or float64 like skimage.img_as_float), transfer, clip to [0,1], round (img_as_ubyte)."""
+    t, r = _stack_u8(targets, "targets"), _stack_u8(references, "references")
+    if t.shape[0] != r.shape[0]:
+        raise ValueError("targets and references must hold the same number of pairs")
+    if out is None:
+        out = np.empty(t.shape, dtype=np.uint8)
+    elif out.shape != t.shape or out.dtype != np.uint8 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous uint8 array of the targets' shape")
+    h = handle or _cabi.default_handle()
+    rc = h.lib.ct_linear_transfer_host_u8(h.h, _METHODS[method], ctypes.c_void_p(t.ctypes.data), ctypes.c_void_p(r.ctypes.data),
+                                          ctypes.c_void_p(out.ctypes.data), t.shape[0], t.shape[1] * t.shape[2],
+                                          r.shape[1] * r.shape[2], 1 if as_float32 else 0)
+    if rc in (_cabi.CT_E_NOT_PD, _cabi.CT_E_SINGULAR):
+        raise np.linalg.LinAlgError(h.lib.ct_last_error(h.h).decode())
+    h.check(rc)
+    return out
+
+
+def idt_frames_u8(targets, references, bins=255, n_iter=4, rotations=None, out=None, as_float32=True, handle=None):
+    """IDT on uint8 frames (see linear_transfer_frames_u8 for the decode / encode convention)."""
+    t, r = _stack_u8(targets, "targets"), _stack_u8(references, "references")
+    b = t.shape[0]
+    if r.shape[0] != b:
+        raise ValueError("targets and references must hold the same number of pairs")
+    if rotations is None:
+        rotations = np.stack([draw_rotations(n_iter) for _ in range(b)])
+    rot = np.ascontiguousarray(rotations, dtype=np.float64).reshape(b, n_iter, 3, 3)
+    if out is None:
+        out = np.empty(t.shape, dtype=np.uint8)
+    elif out.shape != t.shape or out.dtype != np.uint8 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous uint8 array of the targets' shape")
+    h = handle or _cabi.default_handle()
+    rc = h.lib.ct_idt_transfer_host_u8(h.h, ctypes.c_void_p(t.ctypes.data), ctypes.c_void_p(r.ctypes.data),
+                                       ctypes.c_void_p(out.ctypes.data), b, t.shape[1] * t.shape[2], r.shape[1] * r.shape[2],
+                                       1 if as_float32 else 0, ctypes.c_void_p(rot.ctypes.data), int(bins), int(n_iter))
+    if rc == _cabi.CT_E_NONFINITE:
+        raise ValueError("supplied range of projected values is not finite")
+    h.check(rc)
+    return out
 
 
 def _stack(x, name):

@@ -352,6 +352,49 @@ int run_host_pipeline(ct_context *h, const ct_batch *target, const ct_batch *ref
     return CT_OK;
 }
 
+// uint8 frames: [H2D u8 pair] -> u8_to_float x2 -> launch(float pair -> float out) -> float_to_u8 -> [D2H u8]
+// with the same three-stream, two-slot overlap.  `in_dtype` is the float type the frames are
+// decoded to (the semantics of the reference loader being replaced), `out_dtype` what the
+// transfer produces before quantisation.
+template <typename Launch>
+int run_host_pipeline_u8(ct_context *h, const uint8_t *target, const uint8_t *reference, uint8_t *out, int count,
+                         int64_t npix_t, int64_t npix_r, int in_dtype, int out_dtype, Launch &&launch) {
+    const size_t nt = (size_t)npix_t * 3, nr = (size_t)npix_r * 3;
+    const size_t ut = align_up(nt), ur = align_up(nr), uo = align_up(nt);
+    const size_t ft = align_up(nt * elem_size(in_dtype)), fr = align_up(nr * elem_size(in_dtype)), fo = align_up(nt * elem_size(out_dtype));
+    const size_t slot = ut + ur + uo + ft + fr + fo;
+    const int slots = count > 1 ? kSlots : 1;
+    CT_TRY(ensure_stage(h, slot * slots));
+    Pipeline pl;
+    if (pl.init() != 0) return fail(h, CT_E_CUDA, "event creation failed");
+    unsigned char *base = static_cast<unsigned char *>(h->stage);
+    for (int b = 0; b < count; ++b) {
+        const int s = b % slots;
+        unsigned char *p = base + (size_t)s * slot;
+        uint8_t *d_ut = p, *d_ur = p + ut, *d_uo = p + ut + ur;
+        unsigned char *d_ft = p + ut + ur + uo, *d_fr = d_ft + ft, *d_fo = d_fr + fr;
+        if (b >= slots) CT_CUDA(h, cudaStreamWaitEvent(h->copy_in, pl.done[s], 0));
+        CT_CUDA(h, cudaMemcpyAsync(d_ut, target + (size_t)b * nt, nt, cudaMemcpyHostToDevice, h->copy_in));
+        CT_CUDA(h, cudaMemcpyAsync(d_ur, reference + (size_t)b * nr, nr, cudaMemcpyHostToDevice, h->copy_in));
+        CT_CUDA(h, cudaEventRecord(pl.in_ready[s], h->copy_in));
+        CT_CUDA(h, cudaStreamWaitEvent(h->stream, pl.in_ready[s], 0));
+        if (b >= slots) CT_CUDA(h, cudaStreamWaitEvent(h->stream, pl.out_free[s], 0));
+        CT_TRY(launch_u8_to_float(h, d_ut, d_ft, in_dtype, (int64_t)nt));
+        CT_TRY(launch_u8_to_float(h, d_ur, d_fr, in_dtype, (int64_t)nr));
+        ct_batch t1{d_ft, npix_t, 0, 0, 1, in_dtype, CT_HWC, 0}, r1{d_fr, npix_r, 0, 0, 1, in_dtype, CT_HWC, 0};
+        ct_batch o1{d_fo, npix_t, 0, 0, 1, out_dtype, CT_HWC, 0};
+        CT_TRY(launch(b, &t1, &r1, &o1));
+        CT_TRY(launch_float_to_u8(h, d_fo, out_dtype, d_uo, (int64_t)nt));
+        CT_CUDA(h, cudaEventRecord(pl.done[s], h->stream));
+        CT_CUDA(h, cudaStreamWaitEvent(h->copy_out, pl.done[s], 0));
+        CT_CUDA(h, cudaMemcpyAsync(out + (size_t)b * nt, d_uo, nt, cudaMemcpyDeviceToHost, h->copy_out));
+        CT_CUDA(h, cudaEventRecord(pl.out_free[s], h->copy_out));
+    }
+    CT_CUDA(h, cudaStreamSynchronize(h->copy_out));
+    CT_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CT_OK;
+}
+
 int first_bad_status(ct_context *h, const int *dev_status, int B) {
     if (cudaMemcpyAsync(h->host_status, dev_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
         cudaStreamSynchronize(h->stream) != cudaSuccess)
@@ -388,6 +431,49 @@ int ct_linear_transfer_host(ct_handle h, int method, const ct_batch *target, con
                                  return launch_apply(h, method, t, h->xform + (size_t)b * CT_XFORM_DOUBLES, o);
                              }));
     return first_bad_status(h, h->status, target->count);
+}
+
+int ct_linear_transfer_host_u8(ct_handle h, int method, const uint8_t *target, const uint8_t *reference, uint8_t *out,
+                               int32_t count, int64_t npix_target, int64_t npix_reference, int32_t as_float32) {
+    CT_ENTER(h);
+    if (method < CT_REINHARD || method > CT_MKL_CHOLESKY) return fail(h, CT_E_INVALID, "unknown method %d", method);
+    if (!target || !reference || !out || count <= 0 || npix_target <= 0 || npix_reference <= 0)
+        return fail(h, CT_E_INVALID, "bad uint8 batch arguments");
+    CT_TRY(ensure_scratch(h, count));
+    CT_CUDA(h, cudaMemsetAsync(h->status, 0, sizeof(int) * (size_t)count, h->stream));
+    const int in_dtype = as_float32 ? CT_F32 : CT_F64;
+    const int out_dtype = method == CT_REINHARD ? in_dtype : CT_F64;   // the reference's dtype flow
+    CT_TRY(run_host_pipeline_u8(h, target, reference, out, count, npix_target, npix_reference, in_dtype, out_dtype,
+                                [&](int b, const ct_batch *t, const ct_batch *r, const ct_batch *o) {
+                                    CT_TRY(launch_moments(h, t, r, method == CT_REINHARD, h->sums + (size_t)b * 2 * CT_MOMENT_DOUBLES,
+                                                          method, h->xform + (size_t)b * CT_XFORM_DOUBLES, h->status + b));
+                                    return launch_apply(h, method, t, h->xform + (size_t)b * CT_XFORM_DOUBLES, o);
+                                }));
+    return first_bad_status(h, h->status, count);
+}
+
+int ct_idt_transfer_host_u8(ct_handle h, const uint8_t *target, const uint8_t *reference, uint8_t *out, int32_t count,
+                            int64_t npix_target, int64_t npix_reference, int32_t as_float32, const double *rotations,
+                            int32_t bins, int32_t n_iter) {
+    CT_ENTER(h);
+    if (!target || !reference || !out || !rotations || count <= 0 || npix_target <= 0 || npix_reference <= 0)
+        return fail(h, CT_E_INVALID, "bad uint8 batch arguments");
+    if (n_iter < 1 || bins < 1) return fail(h, CT_E_INVALID, "n_iter and bins must be >= 1");
+    if (bins > CT_IDT_MAX_BINS) return fail(h, CT_E_UNSUPPORTED, "bins=%d exceeds CT_IDT_MAX_BINS=%d", bins, CT_IDT_MAX_BINS);
+    CT_TRY(ensure_scratch(h, count));
+    const size_t rot_bytes = align_up(sizeof(double) * (size_t)count * n_iter * 9);
+    const size_t idt_ws = idt_layout(nullptr, npix_target, 1, bins, n_iter).bytes;
+    CT_TRY(ensure_ws(h, rot_bytes + idt_ws));
+    double *d_rot = static_cast<double *>(h->ws);
+    void *idt_base = static_cast<unsigned char *>(h->ws) + rot_bytes;
+    CT_CUDA(h, cudaMemcpyAsync(d_rot, rotations, sizeof(double) * (size_t)count * n_iter * 9, cudaMemcpyHostToDevice, h->stream));
+    CT_CUDA(h, cudaMemsetAsync(h->status, 0, sizeof(int) * (size_t)count, h->stream));
+    CT_TRY(run_host_pipeline_u8(h, target, reference, out, count, npix_target, npix_reference, as_float32 ? CT_F32 : CT_F64, CT_F64,
+                                [&](int b, const ct_batch *t, const ct_batch *r, const ct_batch *o) {
+                                    return idt_run(h, t, r, o, d_rot + (size_t)b * n_iter * 9, bins, n_iter, idt_base, idt_ws,
+                                                   nullptr, h->status + b);
+                                }));
+    return first_bad_status(h, h->status, count);
 }
 
 // ------------------------------------------------------------------ IDT

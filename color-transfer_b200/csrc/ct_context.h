@@ -102,6 +102,10 @@ int launch_solve(ct_context *h, int method, const double *sums_t, const double *
 int launch_apply(ct_context *h, int method, const ct_batch *target, const double *xform,
                  const ct_batch *out);
 
+// ct_u8.cu
+int launch_u8_to_float(ct_context *h, const uint8_t *in, void *out, int dtype, int64_t n);
+int launch_float_to_u8(ct_context *h, const void *in, int dtype, uint8_t *out, int64_t n);
+
 // ct_idt.cu
 int launch_keys_init(ct_context *h, int64_t *keys, int64_t n);
 int launch_ranges(ct_context *h, const ct_batch *img, const double *rot, int64_t rot_stride, int n_rot,

@@ -56,8 +56,10 @@ def frame_pairs_cuda(count, h, w, seed, device, dtype=None, stress=False):
                     field += (u[0] / k) * torch.sin(2 * math.pi * (8 * u[1] * xx + 8 * u[2] * yy) + 2 * math.pi * u[3])
                 g[..., c] = 128 + 96 * field + 8 * torch.randn((h, w), generator=gen, device=device)
             g = g.clamp_(0, 255).floor_()
-        ref[i] = (torch.roll(g, 16, dims=1) / 255.0).to(dtype)
+        # k/255 through float64: torch divides float32 by a scalar as a multiply by 1/255, which is
+        # not the correctly rounded quotient a CPU loader (uint8 / 255) produces
+        ref[i] = (torch.roll(g, 16, dims=1).double() / 255.0).to(dtype)
         gg = torch.rand(6, generator=gen, device=device) * 0.6 + 0.7
         t = (255.0 * gg[:3] * (g / 255.0) ** gg[3:]).clamp_(0, 255).floor_()
-        tgt[i] = (t / 255.0).to(dtype)
+        tgt[i] = (t.double() / 255.0).to(dtype)
     return tgt, ref

@@ -183,6 +183,20 @@ int ct_idt_transfer_host(ct_handle h, const ct_batch *target, const ct_batch *re
                          const ct_batch *out, const double *rotations, int32_t bins,
                          int32_t n_iter, const ct_idt_trace *trace);
 
+/* ------------------------------------------------------------------ uint8 frames
+ * Stacks of `count` interleaved uint8 [npix,3] frames in host memory; 3 bytes per pixel cross
+ * PCIe in each direction.  Frames are decoded exactly as the reference's loaders do
+ * (as_float32 != 0: float32 k/255, ref utils/data.py:106; else float64 k/255.0 as
+ * skimage.img_as_float, ref utils/postprocess.py:138), transferred with the kernels above, and the
+ * result is clipped to [0,1] and rounded to uint8 (np.rint, i.e. img_as_ubyte of the clipped
+ * image, ref utils/postprocess.py:138). */
+int ct_linear_transfer_host_u8(ct_handle h, int method, const uint8_t *target, const uint8_t *reference,
+                               uint8_t *out, int32_t count, int64_t npix_target,
+                               int64_t npix_reference, int32_t as_float32);
+int ct_idt_transfer_host_u8(ct_handle h, const uint8_t *target, const uint8_t *reference, uint8_t *out,
+                            int32_t count, int64_t npix_target, int64_t npix_reference,
+                            int32_t as_float32, const double *rotations, int32_t bins, int32_t n_iter);
+
 #ifdef __cplusplus
 }
 #endif

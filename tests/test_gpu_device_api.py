@@ -136,3 +136,35 @@ def test_runner_contract_host_and_device_paths(mods):
     for i in range(3):
         want = oracle.iterative_distribution_transfer(t[i], r[i])
         assert np.max(np.abs(host[i].permute(1, 2, 0).numpy() - want)) < 1e-6
+
+
+@pytest.mark.parametrize("as_float32", [True, False])
+def test_uint8_frame_io(mods, as_float32):
+    """uint8 frames in / out: decode k/255 as the reference's loaders do, transfer,
+    clip + round like img_as_ubyte.  Compared with the oracle run on the decoded float frames."""
+    torch, _cabi, batch, device, sharded, synth, oracle = mods
+    rng = np.random.default_rng(9)
+    B, H, W = 3, 37, 45
+    pairs = [synthetic_pair(H, W, 400 + i) for i in range(B)]
+    t8 = np.stack([np.rint(p[0] * 255).astype(np.uint8) for p in pairs])
+    r8 = np.stack([np.rint(p[1] * 255).astype(np.uint8) for p in pairs])
+    dt = np.float32 if as_float32 else np.float64
+    tf, rf = (t8 / dt(255)).astype(dt), (r8 / dt(255)).astype(dt)
+
+    def quantise(x):
+        return np.rint(np.clip(x, 0, 1) * 255).astype(np.uint8)
+
+    rot = sharded.predraw_rotations(B, 4, seed=8)
+    out = batch.idt_frames_u8(t8, r8, rotations=rot, as_float32=as_float32)
+    assert out.dtype == np.uint8 and out.shape == t8.shape
+    for i in range(B):
+        want = quantise(oracle.iterative_distribution_transfer(tf[i], rf[i], rotations=rot[i]))
+        assert np.mean(out[i] == want) >= 0.9999
+    for name, fn in (("mkl", oracle.monge_kantorovitch_color_transfer), ("reinhard", oracle.color_transfer_between_images)):
+        out = batch.linear_transfer_frames_u8(name, t8, r8, as_float32=as_float32)
+        for i in range(B):
+            want = quantise(fn(tf[i].astype(np.float64), rf[i].astype(np.float64)))
+            assert np.mean(out[i] == want) >= 0.999
+    # the float path on the decoded frames gives the same bytes
+    again = quantise(batch.idt_frames(tf, rf, rotations=rot))
+    assert np.array_equal(again, batch.idt_frames_u8(t8, r8, rotations=rot, as_float32=as_float32))
