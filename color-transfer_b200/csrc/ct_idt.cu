@@ -13,6 +13,9 @@
 #ifndef CT_MINB
 #define CT_MINB 2
 #endif
+#ifndef CT_RANGES_CHUNK
+#define CT_RANGES_CHUNK 4   // rotations evaluated per pass over a static image (1, 2 or 4)
+#endif
 #ifndef CT_HIST_STAGES
 #define CT_HIST_STAGES 4
 #endif
@@ -127,7 +130,7 @@ __global__ void keys_init_kernel(int64_t *keys, int64_t n) {
 // ---------------------------------------------------------------------------------------------
 // K4: projected range of one image under one rotation (iterative.py:34-35, 39-40)
 // ---------------------------------------------------------------------------------------------
-constexpr int kMaxRot = 4;  // rotations evaluated per pass over an image
+constexpr int kMaxRot = 4;  // most rotations one pass can take
 
 struct RangesArgs {
     Img img;
@@ -140,16 +143,16 @@ struct RangesArgs {
     int32_t *status;
 };
 
-template <typename IO, bool VEC>
+template <typename IO, bool VEC, int NROT>
 __device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const double *rot, int n_rot, RangesPipe &pipe,
-                                             int first_block, int nblocks, double (&mn)[kMaxRot][6], bool &bad) {
+                                             int first_block, int nblocks, double (&mn)[NROT][6], bool &bad) {
     using T = typename IO::elem_t;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
     constexpr int G = IO::G;
     auto group = [&](const double(*x)[3], int n) {
 #pragma unroll
-        for (int k = 0; k < kMaxRot; ++k) {
-            if (k < n_rot) {
+        for (int k = 0; k < NROT; ++k) {
+            if (NROT == 1 || k < n_rot) {
                 double r[9];
 #pragma unroll
                 for (int i = 0; i < 9; ++i) r[i] = rot[9 * k + i];   // shared-memory broadcast
@@ -182,7 +185,8 @@ __device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const 
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) ranges_kernel(RangesArgs a) {
+template <int NROT>  // rotations per pass: registers hold NROT x 6 running minima
+__global__ void __launch_bounds__(kThreads, NROT == 1 ? 3 : 2) ranges_kernel(RangesArgs a) {
     extern __shared__ __align__(16) unsigned char sm_pipe[];
     const int64_t pair = blockIdx.y;
     __shared__ double rot[9 * kMaxRot];
@@ -191,20 +195,20 @@ __global__ void __launch_bounds__(kThreads, 2) ranges_kernel(RangesArgs a) {
     if (threadIdx.x == 0) pipe.init();
     if (threadIdx.x < 9 * a.n_rot) rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
     __syncthreads();
-    double mn[kMaxRot][6];
+    double mn[NROT][6];
 #pragma unroll
-    for (int k = 0; k < kMaxRot; ++k)
+    for (int k = 0; k < NROT; ++k)
 #pragma unroll
         for (int i = 0; i < 6; ++i) mn[k][i] = INFINITY;
     bool bad = false;
     switch (a.kind * 2 + a.vec) {
 #define CT_CASE(ID, T, L, V) \
-    case ID: ranges_image<PixelIO<T, L>, V>(a.img, pair, rot, a.n_rot, pipe, blockIdx.x, gridDim.x, mn, bad); break;
+    case ID: ranges_image<PixelIO<T, L>, V, NROT>(a.img, pair, rot, a.n_rot, pipe, blockIdx.x, gridDim.x, mn, bad); break;
         CT_FOR_EACH_SRC(CT_CASE)
 #undef CT_CASE
     }
 #pragma unroll
-    for (int k = 0; k < kMaxRot; ++k) {
+    for (int k = 0; k < NROT; ++k) {
         if (k < a.n_rot) {
             fold_range(mn[k], a.keys + pair * a.keys_stride + CT_IDT_KEYS * k, red);
             __syncthreads();
@@ -659,11 +663,17 @@ int launch_ranges(ct_context *h, const ct_batch *img, const double *rot, int64_t
     CT_TRY(check_batch(h, img, "images"));
     if (!rot || !keys) return fail(h, CT_E_INVALID, "rot/keys is NULL");
     if (n_rot < 1) return fail(h, CT_E_INVALID, "n_rot must be >= 1");
-    const int nblk = resident_blocks(h, ranges_kernel, pipe_bytes(kRangesStages), img->npix, img->count);
-    for (int k0 = 0; k0 < n_rot; k0 += kMaxRot) {  // kMaxRot rotations per pass over the image
-        const int n = n_rot - k0 < kMaxRot ? n_rot - k0 : kMaxRot;
+    const int chunk = n_rot == 1 ? 1 : CT_RANGES_CHUNK;
+    for (int k0 = 0; k0 < n_rot; k0 += chunk) {  // `chunk` rotations per pass over the image
+        const int n = n_rot - k0 < chunk ? n_rot - k0 : chunk;
         RangesArgs a{img_of(img), src_kind(img), vec_ok(img), n, rot + 9 * k0, rot_stride, keys + CT_IDT_KEYS * k0, keys_stride, status};
-        ranges_kernel<<<dim3(nblk, img->count), kThreads, pipe_bytes(kRangesStages), h->stream>>>(a);
+        if (chunk == 1) {
+            const int nblk = resident_blocks(h, ranges_kernel<1>, pipe_bytes(kRangesStages), img->npix, img->count);
+            ranges_kernel<1><<<dim3(nblk, img->count), kThreads, pipe_bytes(kRangesStages), h->stream>>>(a);
+        } else {
+            const int nblk = resident_blocks(h, ranges_kernel<CT_RANGES_CHUNK>, pipe_bytes(kRangesStages), img->npix, img->count);
+            ranges_kernel<CT_RANGES_CHUNK><<<dim3(nblk, img->count), kThreads, pipe_bytes(kRangesStages), h->stream>>>(a);
+        }
         h->launches++;
         CT_CUDA(h, cudaGetLastError());
     }
