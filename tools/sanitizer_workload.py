@@ -1,0 +1,16 @@
+import sys; import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np
+from conftest import synthetic_pair
+import methods.linear as lin, methods.iterative as it
+from color_transfer_b200 import batch
+for dtype in (np.float32, np.float64):
+    t, r = synthetic_pair(67, 93, 3, dtype, (50, 81))
+    lin.color_transfer_between_images(t, r); lin.monge_kantorovitch_color_transfer(t, r, "cholesky"); lin.color_transfer_in_correlated_color_space(t, r)
+    np.random.seed(1); it.iterative_distribution_transfer(t, r)
+    it.iterative_distribution_transfer(t, r, bins=1024, n_iter=2)
+    tc = np.ascontiguousarray(t.transpose(2,0,1)).transpose(1,2,0); it.iterative_distribution_transfer(tc, r, n_iter=2)
+t, r = synthetic_pair(70, 130, 5, np.float32)   # > one f32 tile (1024 px): exercises the TMA pipeline
+np.random.seed(2); it.iterative_distribution_transfer(t, r)
+t8 = np.rint(np.stack([t, t]) * 255).astype(np.uint8); r8 = np.rint(np.stack([r, r]) * 255).astype(np.uint8)
+batch.idt_frames_u8(t8, r8); batch.linear_transfer_frames_u8("reinhard", t8, r8)
+print("sanitizer workload done")
