@@ -216,3 +216,31 @@ def test_pair0964_all_methods(api, pair0964, golden):
     assert np.max(np.abs(out.reshape(-1)[::stride] - g["idt_sample"])) < 1e-10
     np.random.seed(42)
     _close(out, oracle.iterative_distribution_transfer(left, right))
+
+
+def test_idt_samples_exactly_on_bin_edges(api):
+    """Adversarial for the bin semantics: with axis-aligned rotations the projections of 8-bit
+    images are k/255 and the 255-bin grid over [0,1] has its edges at i*(1/255)+0 - thousands of
+    samples sit exactly on (or one ulp beside) an edge, so every count depends on reproducing
+    np.histogram's comparisons against np.linspace's edges bit for bit."""
+    _, it, oracle = api
+    rng = np.random.default_rng(31)
+    t = rng.integers(0, 256, (96, 128, 3)).astype(np.float64) / 255.0
+    r = rng.integers(0, 256, (80, 112, 3)).astype(np.float64) / 255.0
+    t[0, 0], t[0, 1] = 0.0, 1.0                       # make lo = 0 and hi = 1 exactly on every axis
+    eye = np.eye(3)
+    perm = np.array([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [1.0, 0.0, 0.0]])      # det +1
+    flip = np.array([[-1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.0, 0.0, 1.0]])    # det +1
+    for dtype in (np.float64, np.float32):
+        for bins in (255, 256, 51):
+            rot = np.stack([eye, perm, flip, eye])
+            td, rd = t.astype(dtype), r.astype(dtype)
+            want, traces = oracle.idt_instrumented(td, rd, bins=bins, n_iter=4, rotations=rot)
+            trace = {}
+            out = it.iterative_distribution_transfer(td, rd, bins=bins, n_iter=4, rotations=rot, trace=trace)
+            for i in range(4):
+                assert np.array_equal(trace["counts_t"][i], traces[i]["counts_t"]), (dtype, bins, i)
+                assert np.array_equal(trace["counts_r"][i], traces[i]["counts_r"]), (dtype, bins, i)
+            assert np.array_equal(trace["lo"][0], traces[0]["lo"]) and np.array_equal(trace["hi"][0], traces[0]["hi"])
+            assert np.array_equal(trace["lut"][0], traces[0]["lut"])
+            assert np.max(np.abs(out - want)) < 1e-9
