@@ -137,3 +137,19 @@ def test_rotation_draws_follow_the_reference_rng_stream():
     assert np.array_equal(predraw_rotations(2, 4, seed=42).reshape(8, 3, 3), want)
     np.testing.assert_allclose(np.einsum("nij,nkj->nik", got, got), np.broadcast_to(np.eye(3), (8, 3, 3)), atol=1e-12)
     np.testing.assert_allclose(np.linalg.det(got), 1.0, atol=1e-12)
+
+
+def test_header_is_plain_c_and_library_links_without_python(tmp_path):
+    """gcc (C, not C++) compiles a consumer of include/ct_b200.h, links libct_b200.so and runs it."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    libdir = os.path.join(ROOT, "color-transfer_b200")
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", exe, "-L", libdir, "-lct_b200",
+                    "-Wl,-rpath," + libdir, "-lm"], check=True, capture_output=True, text=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, f"abi_smoke exit code {res.returncode}: {res.stdout}{res.stderr}"
+    assert "abi_smoke ok" in res.stdout
