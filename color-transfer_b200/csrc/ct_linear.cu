@@ -252,7 +252,9 @@ int launch_moments(ct_context *h, const ct_batch *a, const ct_batch *b, int lab,
     const int B = a->count;
     int64_t npix_max = a->npix;
     if (b && b->npix > npix_max) npix_max = b->npix;
-    const int nblk = blocks_for(h, npix_max, 2, (int64_t)B * nimg, 8);
+    // a single pair: one resident wave (3 CTAs/SM) keeps the fixed-order combine short; batches of
+    // small images: more, smaller CTAs balance better
+    const int nblk = blocks_for(h, npix_max, 2, (int64_t)B * nimg, B == 1 ? 3 : 8);
     CT_TRY(ensure_partials(h, (size_t)B * nimg * nblk * 9));
     CT_TRY(ensure_scratch(h, B));
     MomentsArgs m{};
@@ -309,7 +311,7 @@ int launch_apply(ct_context *h, int method, const ct_batch *target, const double
     if (out->layout != CT_HWC) return fail(h, CT_E_UNSUPPORTED, "linear output must be CT_HWC");
     const bool vec = vec_ok(target) && vec_ok(out);
     const int group = target->dtype == CT_F32 ? 4 : 2;
-    const int nblk = blocks_for(h, target->npix, group, target->count, 16);
+    const int nblk = blocks_for(h, target->npix, group, target->count, target->count == 1 ? (method == CT_REINHARD ? 4 : 3) : 16);
     const dim3 grid(nblk, target->count);
     ApplyArgs a{img_of(target), imgout_of(out), xform};
     const bool labm = method == CT_REINHARD;
