@@ -557,7 +557,8 @@ def dropin_pair0964():
     res = {"shape": list(left.shape), "dtype": "float64"}
     cases = (("color_transfer_between_images", methods.linear.color_transfer_between_images, oracle.color_transfer_between_images),
              ("monge_kantorovitch_color_transfer", methods.linear.monge_kantorovitch_color_transfer, oracle.monge_kantorovitch_color_transfer),
-             ("iterative_distribution_transfer", methods.iterative.iterative_distribution_transfer, oracle.iterative_distribution_transfer))
+             ("iterative_distribution_transfer", methods.iterative.iterative_distribution_transfer, oracle.iterative_distribution_transfer),
+             ("automated_color_grading", methods.iterative.automated_color_grading, oracle.automated_color_grading))
     for name, ours, ref in cases:
         np.random.seed(42)
         ours(left, right)

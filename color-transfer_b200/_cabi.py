@@ -64,6 +64,9 @@ SIGNATURES = {
     "ct_linear_apply": (ctypes.c_int, [_P, ctypes.c_int, _BP, _P, _BP]),
     "ct_linear_transfer": (ctypes.c_int, [_P, ctypes.c_int, _BP, _BP, _BP, _P, _P]),
     "ct_linear_transfer_host": (ctypes.c_int, [_P, ctypes.c_int, _BP, _BP, _BP]),
+    "ct_regrain_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32]),
+    "ct_regrain": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, ctypes.c_int32, _P, ctypes.c_size_t]),
+    "ct_acg_transfer_host": (ctypes.c_int, [_P, _BP, _BP, _BP, ctypes.c_int32, ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_int32]),
     "ct_linear_transfer_host_u8": (ctypes.c_int, [_P, ctypes.c_int, _P, _P, _P, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64,
                                                   ctypes.c_int32]),
     "ct_idt_transfer_host_u8": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,

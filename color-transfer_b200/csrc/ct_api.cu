@@ -476,6 +476,63 @@ int ct_idt_transfer_host_u8(ct_handle h, const uint8_t *target, const uint8_t *r
     return first_bad_status(h, h->status, count);
 }
 
+// ------------------------------------------------------------------ regrain / automated colour grading
+size_t ct_regrain_workspace_bytes(int32_t height, int32_t width) {
+    if (height <= 0 || width <= 0) return 0;
+    return regrain_workspace_bytes(height, width);
+}
+
+int ct_regrain(ct_handle h, const double *in, const double *col, double *out, int32_t height, int32_t width,
+               void *workspace, size_t workspace_bytes) {
+    CT_ENTER(h);
+    if (!workspace) {
+        const size_t need = regrain_workspace_bytes(height, width);
+        CT_TRY(ensure_ws(h, need));
+        workspace = h->ws;
+        workspace_bytes = h->ws_bytes;
+    }
+    return launch_regrain(h, in, col, out, height, width, workspace, workspace_bytes);
+}
+
+int ct_acg_transfer_host(ct_handle h, const ct_batch *target, const ct_batch *reference, const ct_batch *out,
+                         int32_t height, int32_t width, const double *rotations, int32_t bins, int32_t n_iter) {
+    CT_ENTER(h);
+    CT_TRY(check_batch(h, target, "target"));
+    CT_TRY(check_batch(h, reference, "reference"));
+    CT_TRY(check_batch(h, out, "out"));
+    if (target->count != 1 || reference->count != 1 || out->count != 1) return fail(h, CT_E_UNSUPPORTED, "automated colour grading takes one pair per call");
+    if ((int64_t)height * width != target->npix || out->npix != target->npix) return fail(h, CT_E_INVALID, "height * width must equal target.npix and out.npix");
+    if (out->dtype != CT_F64 || out->layout != CT_HWC) return fail(h, CT_E_INVALID, "output must be float64 CT_HWC");
+    if (!rotations) return fail(h, CT_E_INVALID, "rotations is NULL");
+    if (n_iter < 1 || bins < 1) return fail(h, CT_E_INVALID, "n_iter and bins must be >= 1");
+    if (bins > CT_IDT_MAX_BINS) return fail(h, CT_E_UNSUPPORTED, "bins=%d exceeds CT_IDT_MAX_BINS=%d", bins, CT_IDT_MAX_BINS);
+    CT_TRY(ensure_scratch(h, 1));
+    const size_t tb = align_up(image_bytes(target)), rb = align_up(image_bytes(reference));
+    const size_t fb = align_up(sizeof(double) * 3 * (size_t)target->npix);
+    CT_TRY(ensure_stage(h, tb + rb + 3 * fb));
+    unsigned char *st = static_cast<unsigned char *>(h->stage);
+    unsigned char *d_t = st, *d_r = st + tb;
+    double *d_col = reinterpret_cast<double *>(st + tb + rb), *d_in = d_col + fb / 8, *d_res = d_in + fb / 8;
+    const size_t rot_bytes = align_up(sizeof(double) * (size_t)n_iter * 9);
+    const size_t idt_ws = idt_layout(nullptr, target->npix, 1, bins, n_iter).bytes;
+    const size_t rg_ws = regrain_workspace_bytes(height, width);
+    const size_t ws_need = rot_bytes + (idt_ws > rg_ws ? idt_ws : rg_ws);
+    CT_TRY(ensure_ws(h, ws_need));
+    double *d_rot = static_cast<double *>(h->ws);
+    void *ws = static_cast<unsigned char *>(h->ws) + rot_bytes;
+    CT_CUDA(h, cudaMemcpyAsync(d_t, target->data, image_bytes(target), cudaMemcpyHostToDevice, h->stream));
+    CT_CUDA(h, cudaMemcpyAsync(d_r, reference->data, image_bytes(reference), cudaMemcpyHostToDevice, h->stream));
+    CT_CUDA(h, cudaMemcpyAsync(d_rot, rotations, sizeof(double) * (size_t)n_iter * 9, cudaMemcpyHostToDevice, h->stream));
+    CT_CUDA(h, cudaMemsetAsync(h->status, 0, sizeof(int), h->stream));
+    const ct_batch t1 = single(target, d_t), r1 = single(reference, d_r);
+    ct_batch c1{d_col, target->npix, 0, 0, 1, CT_F64, CT_HWC, 0};
+    CT_TRY(idt_run(h, &t1, &r1, &c1, d_rot, bins, n_iter, ws, ws_need - rot_bytes, nullptr, h->status));   // iterative.py:135
+    CT_TRY(launch_to_f64_hwc(h, &t1, d_in));
+    CT_TRY(launch_regrain(h, d_in, d_col, d_res, height, width, ws, ws_need - rot_bytes));                  // iterative.py:136
+    CT_CUDA(h, cudaMemcpyAsync(out->data, d_res, sizeof(double) * 3 * (size_t)target->npix, cudaMemcpyDeviceToHost, h->stream));
+    return first_bad_status(h, h->status, 1);
+}
+
 // ------------------------------------------------------------------ IDT
 int64_t ct_idt_key_of(double value) { return key_of(value); }
 double ct_idt_value_of(int64_t key) { return value_of(key); }

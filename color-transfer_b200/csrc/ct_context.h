@@ -106,6 +106,12 @@ int launch_apply(ct_context *h, int method, const ct_batch *target, const double
 int launch_u8_to_float(ct_context *h, const uint8_t *in, void *out, int dtype, int64_t n);
 int launch_float_to_u8(ct_context *h, const void *in, int dtype, uint8_t *out, int64_t n);
 
+// ct_regrain.cu
+size_t regrain_workspace_bytes(int H, int W);
+int launch_regrain(ct_context *h, const double *in, const double *col, double *out, int H, int W, void *workspace,
+                   size_t workspace_bytes);
+int launch_to_f64_hwc(ct_context *h, const ct_batch *img, double *out);
+
 // ct_idt.cu
 int launch_keys_init(ct_context *h, int64_t *keys, int64_t n);
 int launch_ranges(ct_context *h, const ct_batch *img, const double *rot, int64_t rot_stride, int n_rot,

@@ -4,8 +4,8 @@ Mirror of ref: methods/iterative.py:8-59 (``iterative_distribution_transfer``). 
 rotations are drawn here, on the host, with the very call the reference makes
 (``scipy.stats.special_ortho_group.rvs(3)`` once per iteration, in order), so the global numpy
 RNG advances exactly as in the reference and ``np.random.seed(s)`` reproduces its matrices.
-Regrain / ``automated_color_grading`` (ref: methods/iterative.py:62-138) is outside the hot
-path and is not provided.
+``automated_color_grading`` = IDT + regrain (ref: methods/iterative.py:62-138, SURVEY.md
+section 8f-2) runs on the device in one call as well.
 """
 
 import ctypes
@@ -15,7 +15,7 @@ import scipy.stats
 
 from .. import _cabi
 
-__all__ = ["iterative_distribution_transfer", "draw_rotations"]
+__all__ = ["iterative_distribution_transfer", "automated_color_grading", "draw_rotations"]
 
 
 def draw_rotations(n_iter, n_dims=3):
@@ -79,6 +79,38 @@ def iterative_distribution_transfer(target, reference, bins=255, n_iter=4, *, ro
         raise ValueError("supplied range of projected values is not finite")  # np.histogram, _get_outer_edges
     if rc == _cabi.CT_E_UNSUPPORTED:
         raise NotImplementedError(h.lib.ct_last_error(h.h).decode())
+    h.check(rc)
+    del t_keep, r_keep
+    return out
+
+
+def automated_color_grading(target, reference, *, rotations=None, out=None, handle=None):
+    """Automated Colour Grading using Colour Distribution Transfer (Pitie et al., 2007) -
+    ref: methods/iterative.py:118-138: ``iterative_distribution_transfer(target, reference)``
+    followed by the gradient-preserving regrain of the original target.  float64 ``[H,W,3]``."""
+    t = np.asarray(target)
+    r = np.asarray(reference)
+    if t.ndim != 3 or r.ndim != 3 or t.shape[-1] != 3 or r.shape[-1] != 3:
+        raise ValueError("target and reference must have shape [H, W, 3]")
+    if t.dtype != np.float32 and t.dtype != np.float64:
+        t = t.astype(np.float64)
+    if r.dtype != np.float32 and r.dtype != np.float64:
+        r = r.astype(np.float64)
+    n_iter, bins = 4, 255                       # the reference calls IDT with its defaults
+    if rotations is None:
+        rotations = draw_rotations(n_iter)
+    rot = np.ascontiguousarray(rotations, dtype=np.float64).reshape(n_iter, 3, 3)
+    if out is None:
+        out = np.empty(t.shape, dtype=np.float64)
+    elif out.shape != t.shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous float64 array of the target's shape")
+    h = handle or _cabi.default_handle()
+    tb, t_keep = _cabi.batch_from_numpy(t)
+    rb, r_keep = _cabi.batch_from_numpy(r)
+    ob, _ = _cabi.batch_from_numpy(out)
+    rc = h.lib.ct_acg_transfer_host(h.h, tb, rb, ob, t.shape[0], t.shape[1], ctypes.c_void_p(rot.ctypes.data), bins, n_iter)
+    if rc == _cabi.CT_E_NONFINITE:
+        raise ValueError("supplied range of projected values is not finite")
     h.check(rc)
     del t_keep, r_keep
     return out

@@ -183,6 +183,16 @@ int ct_idt_transfer_host(ct_handle h, const ct_batch *target, const ct_batch *re
                          const ct_batch *out, const double *rotations, int32_t bins,
                          int32_t n_iter, const ct_idt_trace *trace);
 
+/* ------------------------------------------------------------------ regrain
+ * _regrain(img_arr_in, img_arr_col) of ref methods/iterative.py:62-115 on device fp64 [H][W][3]
+ * images (multigrid pyramid by skimage.transform.resize semantics + Jacobi relaxation), and
+ * automated_color_grading = IDT + regrain (iterative.py:118-138) from host buffers. */
+size_t ct_regrain_workspace_bytes(int32_t height, int32_t width);
+int ct_regrain(ct_handle h, const double *in, const double *col, double *out, int32_t height, int32_t width,
+               void *workspace, size_t workspace_bytes);
+int ct_acg_transfer_host(ct_handle h, const ct_batch *target, const ct_batch *reference, const ct_batch *out,
+                         int32_t height, int32_t width, const double *rotations, int32_t bins, int32_t n_iter);
+
 /* ------------------------------------------------------------------ uint8 frames
  * Stacks of `count` interleaved uint8 [npix,3] frames in host memory; 3 bytes per pixel cross
  * PCIe in each direction.  Frames are decoded exactly as the reference's loaders do

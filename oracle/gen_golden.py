@@ -10,7 +10,7 @@ bit-identical arrays for Xiao / MKL / IDT, and the reference's outputs are store
 committed fixtures are what pins the oracle on machines without /root/reference.
 
 Cases
-  small_f64 / small_f32 : seeded 24x40 synthetic stereo pair, all functions, full outputs
+  small_f64 / small_f32 : seeded 48x56 synthetic stereo pair, all functions, full outputs
                           and full IDT traces (rotations, ranges, counts, LUTs).
   pair0964              : graphics/0964_{L,R}.png (copied to tests/golden/), float64;
                           covariances, the three MKL matrices, IDT ranges/counts/LUTs after
@@ -96,8 +96,13 @@ def run_case(ref_lin, ref_it, tgt, ref, full):
     out["idt_b64_n2"] = ref_it.iterative_distribution_transfer(tgt, ref, bins=64, n_iter=2)
     np.random.seed(IDT_SEED + 1)
     _same(out["idt_b64_n2"], oracle.iterative_distribution_transfer(tgt, ref, 64, 2), "idt b64")
+    # automated colour grading = IDT + regrain (the reference code with the restated resize)
+    np.random.seed(IDT_SEED)
+    out["acg"] = ref_it.automated_color_grading(tgt, ref)
+    np.random.seed(IDT_SEED)
+    _same(out["acg"], oracle.automated_color_grading(tgt, ref), "automated_color_grading")
     if not full:
-        for k in ("reinhard", "ccs", "mkl_MK", "mkl_sqrt", "mkl_cholesky", "idt", "idt_b64_n2"):
+        for k in ("reinhard", "ccs", "mkl_MK", "mkl_sqrt", "mkl_cholesky", "idt", "idt_b64_n2", "acg"):
             v = out.pop(k)
             out[k + "_sample"] = v.reshape(-1)[::SAMPLE_STRIDE].copy()
             out[k + "_stats"] = np.array([v.min(), v.max(), v.mean()])
@@ -113,7 +118,7 @@ def main():
     ref_lin, ref_it = load_reference.linear(), load_reference.iterative()
     os.makedirs(GOLDEN, exist_ok=True)
     for name, dtype in (("small_f64", np.float64), ("small_f32", np.float32)):
-        tgt, ref = synthetic_pair(24, 40, 7, dtype)
+        tgt, ref = synthetic_pair(48, 56, 7, dtype)          # > 40 px per side: the regrain pyramid has 2 levels
         res = run_case(ref_lin, ref_it, tgt, ref, full=True)
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), target=tgt, reference=ref, **res)
         print(name, {k: (v.shape, str(v.dtype)) for k, v in res.items() if k in ("reinhard", "idt", "ccs")})

@@ -12,7 +12,8 @@ a stub ``skimage`` on ``sys.modules`` for the duration of the load:
 * ``skimage.color.rgb2lab / lab2rgb`` -> oracle/skimage_color.py (restatement, so the
   Reinhard function is "reference data flow + restated Lab"; Xiao / MKL / IDT do not touch
   skimage at all and run as pure reference code);
-* ``skimage.transform.resize`` -> raises (only the out-of-scope regrain uses it).
+* ``skimage.transform.resize`` -> oracle/skimage_resize.py (restated wrapper over the real
+  scipy.ndimage), used by the regrain of ``automated_color_grading``.
 """
 
 import importlib.util
@@ -38,10 +39,8 @@ def _stub_skimage():
     color.lab2rgb = skimage_color.lab2rgb
     transform = types.ModuleType("skimage.transform")
 
-    def resize(*_a, **_k):
-        raise NotImplementedError("skimage.transform.resize is not restated (regrain is out of scope)")
-
-    transform.resize = resize
+    from . import skimage_resize
+    transform.resize = skimage_resize.resize
     pkg.color, pkg.transform = color, transform
     return {"skimage": pkg, "skimage.color": color, "skimage.transform": transform}
 

@@ -13,6 +13,8 @@ indices) can be inspected:
 * Xiao correlated colour space        ref: methods/linear.py:45-82
 * Pitie Monge-Kantorovitch            ref: methods/linear.py:85-124
 * Pitie iterative distribution transfer  ref: methods/iterative.py:8-59
+* regrain / automated colour grading     ref: methods/iterative.py:62-138 (its
+  ``skimage.transform.resize`` is the restated wrapper over scipy.ndimage, oracle/skimage_resize.py)
 
 Pinning: ``oracle/gen_golden.py`` executes the UNMODIFIED reference files
 (loaded by path from /root/reference, see oracle/load_reference.py) on seeded
@@ -28,7 +30,7 @@ import numpy as np
 import scipy.linalg
 import scipy.stats
 
-from . import skimage_color
+from . import skimage_color, skimage_resize
 
 # --------------------------------------------------------------------------- linear
 
@@ -215,3 +217,51 @@ def idt_instrumented(target, reference, bins=255, n_iter=4, rotations=None, keep
 def iterative_distribution_transfer(target, reference, bins=255, n_iter=4, rotations=None):
     """Pitie, Kokaram & Dahyot 2007.  ref: methods/iterative.py:8-59."""
     return idt_instrumented(target, reference, bins, n_iter, rotations, keep_arrays=False)[0]
+
+
+# --------------------------------------------------------------------------- regrain (ACG)
+
+REGRAIN_SWEEPS = (4, 16, 32, 64, 64, 64)
+
+
+def _neighbours(a):
+    """(next column, next row, previous column, previous row) with the edge replicated - the
+    reference's last_pad_1 / last_pad_0 / first_pad_1 / first_pad_0 (iterative.py:87-90)."""
+    p = np.pad(a, ((1, 1), (1, 1), (0, 0)), mode="edge")
+    return p[1:-1, 2:], p[2:, 1:-1], p[1:-1, :-2], p[:-2, 1:-1]
+
+
+def regrain_relax(out, src, col, sweeps, level, eps=1e-6):
+    """`sweeps` Jacobi sweeps of the gradient-preserving relaxation.  ref: methods/iterative.py:80-115."""
+    s_e, s_s, s_w, s_n = _neighbours(src)
+    grad = np.sqrt(((s_e - s_w) ** 2 + (s_s - s_n) ** 2).sum(axis=2, keepdims=True))
+    psi = 256 * grad / 5
+    psi[psi > 1] = 1
+    phi = 30 * 2 ** (-level) / (1 + 10 * grad)
+    p_e, p_s, p_w, p_n = _neighbours(phi)
+    phi1, phi2, phi3, phi4 = (p_e + phi) / 2, (p_s + phi) / 2, (p_w + phi) / 2, (p_n + phi) / 2
+    rho = 1 / 5.0
+    for _ in range(sweeps):
+        o_e, o_s, o_w, o_n = _neighbours(out)
+        den = psi + phi1 + phi2 + phi3 + phi4
+        num = (psi * col + phi1 * (o_e - s_e + src) + phi2 * (o_s - s_s + src)
+               + phi3 * (o_w - s_w + src) + phi4 * (o_n - s_n + src))
+        out = num / (den + eps) * (1 - rho) + rho * out
+    return out
+
+
+def regrain(src, col, sweeps=REGRAIN_SWEEPS, level=0):
+    """Multigrid regrain.  ref: methods/iterative.py:62-77."""
+    h, w, _ = src.shape
+    h2, w2 = (h + 1) // 2, (w + 1) // 2
+    if len(sweeps) > 1 and h2 > 20 and w2 > 20:
+        coarse = regrain(skimage_resize.resize(src, (h2, w2)), skimage_resize.resize(col, (h2, w2)), sweeps[1:], level + 1)
+        start = skimage_resize.resize(coarse, (h, w))
+    else:
+        start = src
+    return regrain_relax(start, src, col, sweeps[0], level)
+
+
+def automated_color_grading(target, reference, rotations=None):
+    """Pitie, Kokaram & Dahyot 2007.  ref: methods/iterative.py:118-138."""
+    return regrain(target, iterative_distribution_transfer(target, reference, rotations=rotations))

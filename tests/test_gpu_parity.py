@@ -244,3 +244,35 @@ def test_idt_samples_exactly_on_bin_edges(api):
             assert np.array_equal(trace["lo"][0], traces[0]["lo"]) and np.array_equal(trace["hi"][0], traces[0]["hi"])
             assert np.array_equal(trace["lut"][0], traces[0]["lut"])
             assert np.max(np.abs(out - want)) < 1e-9
+
+
+@pytest.mark.parametrize("h,w", [(48, 56), (97, 131), (41, 43), (200, 333)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_automated_color_grading(api, h, w, dtype):
+    """IDT + regrain (ref: methods/iterative.py:118-138) against the oracle, whose
+    resize is the restated skimage wrapper over the real scipy.ndimage."""
+    _, it, oracle = api
+    t, r = synthetic_pair(h, w, 61, dtype)
+    np.random.seed(13)
+    want = oracle.automated_color_grading(t.astype(np.float64), r.astype(np.float64))
+    np.random.seed(13)
+    out = it.automated_color_grading(t.astype(np.float64), r.astype(np.float64)) if dtype == np.float64 else None
+    if dtype == np.float64:
+        assert out.dtype == np.float64 and out.shape == t.shape
+        assert np.max(np.abs(out - want)) < 1e-9
+    else:
+        # float32 input: the reference keeps its pyramid of `target` in float32; gate against the
+        # float64 oracle like the linear functions (SURVEY 0.5)
+        np.random.seed(13)
+        out = it.automated_color_grading(t, r)
+        _close(out, want, u8=0.999)
+
+
+def test_automated_color_grading_pair0964(api, pair0964, golden):
+    _, it, oracle = api
+    left, right = pair0964
+    np.random.seed(42)
+    out = it.automated_color_grading(left, right)
+    g = golden["pair0964"]
+    assert np.max(np.abs(out.reshape(-1)[::997] - g["acg_sample"])) < 1e-8
+    assert abs(out.mean() - g["acg_stats"][2]) < 1e-9

@@ -35,6 +35,8 @@ def test_oracle_matches_golden_small(golden, case):
     assert np.array_equal(np.stack([x["lo"] for x in traces]), g["idt_lo"])
     np.random.seed(IDT_SEED + 1)
     assert np.array_equal(oracle.iterative_distribution_transfer(t, r, 64, 2), g["idt_b64_n2"])
+    np.random.seed(IDT_SEED)
+    assert np.array_equal(oracle.automated_color_grading(t, r), g["acg"])        # IDT + regrain
 
 
 def test_oracle_matches_golden_pair0964(golden, pair0964):
@@ -118,6 +120,35 @@ def test_lab_agrees_with_opencv():
     ours = skimage_color.rgb2lab(rgb.astype(np.float64))
     theirs = cv2.cvtColor(rgb, cv2.COLOR_RGB2Lab)       # OpenCV's own (approximate) implementation
     assert np.max(np.abs(ours - theirs)) < 0.5
+
+
+def test_resize_restatement_shapes_and_identities():
+    """oracle/skimage_resize.py: defaults of skimage.transform.resize over the real scipy.ndimage."""
+    from oracle import skimage_resize
+    rng = np.random.default_rng(4)
+    img = rng.random((45, 62, 3))
+    small = skimage_resize.resize(img, (23, 31))
+    assert small.shape == (23, 31, 3) and small.dtype == np.float64
+    assert img.min() <= small.min() and small.max() <= img.max()              # clip=True
+    assert np.array_equal(skimage_resize.resize(img, (45, 62)), img)          # same size: identity
+    flat = np.full((40, 40, 3), 0.37)
+    assert np.allclose(skimage_resize.resize(flat, (20, 20)), 0.37, atol=1e-15)
+    up = skimage_resize.resize(small, (45, 62))
+    assert up.shape == img.shape and np.abs(up - img).mean() < 0.3
+    ramp = np.repeat(np.linspace(0, 1, 64)[None, :, None], 8, axis=0).repeat(3, axis=2)
+    half = skimage_resize.resize(ramp, (8, 32))                               # linear ramps survive away from the border
+    assert np.allclose(half[:, 4:-4, 0], (ramp[:, 8:-8:2, 0] + ramp[:, 9:-7:2, 0]) / 2, atol=1e-12)
+
+
+@pytest.mark.skipif(not skimage_color.have_real_skimage, reason="scikit-image is not installed")
+def test_resize_restatement_equals_scikit_image():
+    from skimage.transform import resize
+
+    from oracle import skimage_resize
+    rng = np.random.default_rng(5)
+    img = rng.random((45, 62, 3))
+    assert np.max(np.abs(resize(img, (23, 31)) - skimage_resize.resize(img, (23, 31)))) < 1e-12
+    assert np.max(np.abs(resize(img[:23, :31], (45, 62)) - skimage_resize.resize(img[:23, :31], (45, 62)))) < 1e-12
 
 
 @pytest.mark.skipif(not skimage_color.have_real_skimage, reason="scikit-image is not installed")

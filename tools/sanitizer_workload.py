@@ -13,4 +13,6 @@ t, r = synthetic_pair(70, 130, 5, np.float32)   # > one f32 tile (1024 px): exer
 np.random.seed(2); it.iterative_distribution_transfer(t, r)
 t8 = np.rint(np.stack([t, t]) * 255).astype(np.uint8); r8 = np.rint(np.stack([r, r]) * 255).astype(np.uint8)
 batch.idt_frames_u8(t8, r8); batch.linear_transfer_frames_u8("reinhard", t8, r8)
+t, r = synthetic_pair(97, 131, 7, np.float64)
+np.random.seed(3); it.automated_color_grading(t, r)
 print("sanitizer workload done")
