@@ -337,8 +337,9 @@ __device__ void build_lut(const LutArgs &a, int64_t pair, double *sm) {
         if (threadIdx.x == 0) {
             double *tail = lut + (int64_t)9 * CT_IDT_EDGE_STRIDE(bins) + 4 * j;
             tail[0] = g.lo; tail[1] = g.hi; tail[2] = g.step; tail[3] = g.inv;
-            if (a.tr_lo) a.tr_lo[tr_base + j] = g.lo;
-            if (a.tr_hi) a.tr_hi[tr_base + j] = g.hi;
+            // the trace reports the data range itself (before np.histogram widens lo == hi)
+            if (a.tr_lo) a.tr_lo[tr_base + j] = value_of(__ldcg(a.keys + pair * a.keys_stride + j));
+            if (a.tr_hi) a.tr_hi[tr_base + j] = -value_of(__ldcg(a.keys + pair * a.keys_stride + 3 + j));
         }
         __syncthreads();
     }

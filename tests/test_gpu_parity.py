@@ -276,3 +276,30 @@ def test_automated_color_grading_pair0964(api, pair0964, golden):
     g = golden["pair0964"]
     assert np.max(np.abs(out.reshape(-1)[::997] - g["acg_sample"])) < 1e-8
     assert abs(out.mean() - g["acg_stats"][2]) < 1e-9
+
+
+def test_idt_degenerate_ranges(api):
+    """lo == hi on every axis (np.histogram widens the range by +-0.5, _histograms_impl.py:321-324),
+    a constant reference, and identical images."""
+    import warnings
+    _, it, oracle = api
+    rng = np.random.default_rng(41)
+    varied, _ = synthetic_pair(24, 28, 42)
+    const_a, const_b = np.full((24, 28, 3), 0.25), np.full((20, 20, 3), 0.25)
+    cases = {"both constant and equal": (const_a, const_b), "constant reference": (varied, np.full((20, 20, 3), 0.6)),
+             "identical images": (varied, varied.copy())}
+    for name, (t, r) in cases.items():
+        rot = np.stack([oracle.draw_rotation() for _ in range(3)]) if False else None
+        np.random.seed(17)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want, traces = oracle.idt_instrumented(t, r, n_iter=3)
+        np.random.seed(17)
+        trace = {}
+        out = it.iterative_distribution_transfer(t, r, n_iter=3, trace=trace)
+        assert np.array_equal(trace["counts_t"][0], traces[0]["counts_t"]), name
+        assert np.array_equal(trace["counts_r"][0], traces[0]["counts_r"]), name
+        assert np.array_equal(trace["lo"][0], traces[0]["lo"]) and np.array_equal(trace["hi"][0], traces[0]["hi"]), name
+        assert np.array_equal(np.isnan(out), np.isnan(want)), name
+        ok = ~np.isnan(want)
+        assert np.max(np.abs(out[ok] - want[ok]), initial=0.0) < 1e-6, name
