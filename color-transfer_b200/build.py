@@ -26,11 +26,12 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    extra = os.environ.get("CT_NVCC_DEFS", "").split()   # tuning experiments: -DCT_...=n
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

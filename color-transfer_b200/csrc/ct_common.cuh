@@ -59,8 +59,9 @@ struct PixelIO {
             x[2] = (double)img[2 * plane + p];
         }
     }
+    template <typename X>
     __device__ __forceinline__ static void store1(T *img, int64_t plane, int64_t p,
-                                                  const double (&x)[3]) {
+                                                  const X (&x)[3]) {
         if (LAYOUT == CT_HWC) {
             img[3 * p + 0] = (T)x[0];
             img[3 * p + 1] = (T)x[1];
@@ -123,9 +124,9 @@ struct PixelIO {
     }
 
     // store GS pixels starting at pixel p0 (GS is the SOURCE group size; p0 % GS == 0)
-    template <bool VEC, int GS>
+    template <bool VEC, int GS, typename X>
     __device__ __forceinline__ static void store(T *img, int64_t plane, int64_t p0,
-                                                 const double (&x)[GS][3]) {
+                                                 const X (&x)[GS][3]) {
         if (!VEC || GS % G != 0) {  // narrower source group than one destination vector
 #pragma unroll
             for (int i = 0; i < GS; ++i) store1(img, plane, p0 + i, x[i]);

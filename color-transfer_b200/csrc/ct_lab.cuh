@@ -10,8 +10,8 @@
 //     result x^2.4 = (x*y)^3 (n=5),  cbrt x = x*y^2 (n=3),  x^(5/12) = x*y^7 (n=12)
 // i.e. 3-4 XU operations per power instead of 7 (pow() would be ~150 fp64 instructions).
 //
-// The statistics pass (mean / std over millions of pixels) uses the fp32 chain alone: its
-// per-pixel error (~3e-7 relative) shifts the Lab means by ~1e-5 of a Lab unit, 1e-7 in RGB.
+// That fp64 chain serves float64 images.  The statistics pass (mean / std over millions of
+// pixels) and the whole float32-image remap use the fp32 chain at the end of this file.
 #pragma once
 
 #include "ct_common.cuh"
@@ -54,23 +54,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
 #define CT_XYZ_ROW0(T, a, b, c) ((T)(0.412453 / 0.95047) * (a) + (T)(0.357580 / 0.95047) * (b) + (T)(0.180423 / 0.95047) * (c))
 #define CT_XYZ_ROW1(T, a, b, c) ((T)0.212671 * (a) + (T)0.715160 * (b) + (T)0.072169 * (c))
 #define CT_XYZ_ROW2(T, a, b, c) ((T)(0.019334 / 1.08883) * (a) + (T)(0.119193 / 1.08883) * (b) + (T)(0.950227 / 1.08883) * (c))
-
-// ------------------------------------------------------------------ fp32 chain (statistics, seeds)
-__device__ __forceinline__ float srgb_decode_f(float v) {
-    return v > 0.04045f ? ex2_approx(2.4f * lg2_approx((v + 0.055f) * (1.0f / 1.055f))) : v * (1.0f / 12.92f);
-}
-__device__ __forceinline__ float lab_f_f(float t) {
-    return t > 0.008856f ? ex2_approx(0.33333334f * lg2_approx(t)) : fmaf(7.787f, t, 16.0f / 116.0f);
-}
-__device__ __forceinline__ void rgb2lab_f32(const float (&rgb)[3], float (&out)[3]) {
-    const float l0 = srgb_decode_f(rgb[0]), l1 = srgb_decode_f(rgb[1]), l2 = srgb_decode_f(rgb[2]);
-    const float fx = lab_f_f(CT_XYZ_ROW0(float, l0, l1, l2));
-    const float fy = lab_f_f(CT_XYZ_ROW1(float, l0, l1, l2));
-    const float fz = lab_f_f(CT_XYZ_ROW2(float, l0, l1, l2));
-    out[0] = fmaf(116.0f, fy, -16.0f);
-    out[1] = 500.0f * (fx - fy);
-    out[2] = 200.0f * (fy - fz);
-}
 
 // ------------------------------------------------------------------ fp64 chain, fp32 seeds
 // The seed of each power needs its operand as a float: one F2F (XU) per power, except for the
@@ -143,6 +126,124 @@ __device__ __forceinline__ void lab2rgb(const double (&labv)[3], double (&rgb)[3
     rgb[0] = srgb_encode(fma(kL.r0[2], Z, fma(kL.r0[1], Y, kL.r0[0] * X)));
     rgb[1] = srgb_encode(fma(kL.r1[2], Z, fma(kL.r1[1], Y, kL.r1[0] * X)));
     rgb[2] = srgb_encode(fma(kL.r2[2], Z, fma(kL.r2[1], Y, kL.r2[0] * X)));
+}
+
+
+// ------------------------------------------------------------------ float32 images: fp32 chain
+// Reinhard on float32 images (the dtype of the reference's CLI path) returns float32 and only has
+// to land within 1e-4 / 99.99 % uint8 of the float64 oracle (the reference's own float32 path is
+// 1e-4 away from it), so the whole remap runs in fp32: 126 instructions per pixel
+// instead of 340, no F2F conversions.  What decides the accuracy is the cube root: its error is
+// amplified ~4.4x by the cancelling rows of rgb_from_xyz, so the MUFU seed (2.5 ulp as t z^2) is
+// polished by one Newton step ON y = cbrt t (residual by FMA): 0.7 ulp.  Emulated on the CPU
+// (tools/emulate_reinhard_fp32.py): mean |err| 1.2e-7, uint8 flips 2.8e-5 - the same as with a
+// correctly rounded fp32 cbrt; without the polish 5.4e-7 / 1.2e-4 (gate missed); with fp64
+// between the two matrices 0.9e-7 / 2.3e-5 at twice the instructions.
+
+// float thresholds are the doubles rounded DOWN, so that `xf > c_f` decides like `(double)xf > c`
+#define CT_THR_DEC_F 0.040449999272823334f
+#define CT_THR_F_F 0.008855999447405338f
+#define CT_THR_FINV_F 0.2068965882062912f
+#define CT_THR_ENC_F 0.0031307998578995466f
+
+// u^2.4 = u^2 * u^0.4: the 0.4 keeps the lg2 error (2^-22 relative) from being amplified.  The
+// statistics pass (FAST) takes ex2(2.4 lg2 u) directly: its errors average out over the image.
+template <bool FAST>
+__device__ __forceinline__ float srgb_decode_h(float v) {
+    const float u = fmaf(v, 1.0f / 1.055f, 0.055f / 1.055f);
+    const float lg = lg2_approx(u);
+    const float hi = FAST ? ex2_approx(2.4f * lg) : (u * u) * ex2_approx(0.4f * lg);
+    return v > CT_THR_DEC_F ? hi : v * (1.0f / 12.92f);
+}
+
+// t^(-1/3), t > 0, on the FMA pipe alone: integer seed (3.4 %), then one degree-5 correction
+// y (1 + r P(r)), r = 1 - t y^3, P a Chebyshev fit of ((1-r)^(-1/3) - 1) / r over |r| < 0.107:
+// 2.5e-7 max, bias 3e-9 (11 instructions, no XU) - the XU pipe is what the Lab kernels run out of
+__device__ __forceinline__ float rcbrt_fma(float t) {
+    const float y = __uint_as_float(0x54a23000u - __umulhi(__float_as_uint(t), 0x55555556u));
+    const float r = fmaf(-t, (y * y) * y, 1.0f);
+    float p = fmaf(r, 0.1244070650f, 0.1453286727f);
+    p = fmaf(r, p, 0.1728475290f);
+    p = fmaf(r, p, 0.2222193078f);
+    p = fmaf(r, p, 0.3333333260f);
+    return fmaf(y * r, p, y);
+}
+__device__ __forceinline__ float rcbrt_xu(float t) { return ex2_approx(-0.33333334f * lg2_approx(t)); }
+
+// xyz2lab's f(): cbrt(t) for t > 0.008856, else 7.787 t + 16/116.  FMA_SEED picks the pipe of
+// the seed, POLISH adds the Newton step (the remap needs it, the statistics pass does not)
+template <bool FMA_SEED, bool POLISH>
+__device__ __forceinline__ float lab_f_h(float t) {
+    const float z = FMA_SEED ? rcbrt_fma(t) : rcbrt_xu(t);
+    const float zz = z * z;
+    float y = t * zz;
+    if (POLISH) y = fmaf(fmaf(-y * y, y, t), zz * 0.33333334f, y);  // y + (t - y^3) / (3 y^2)
+    return t > CT_THR_F_F ? y : fmaf(7.787f, t, 16.0f / 116.0f);
+}
+
+__device__ __forceinline__ float finv_h(float f) {
+    return f > CT_THR_FINV_F ? (f * f) * f : fmaf(f, 1.0f / 7.787f, -(16.0f / 116.0f) / 7.787f);
+}
+
+// np.clip(s, 0, 1) in two instructions; the .NaN forms keep a NaN a NaN, like np.clip
+__device__ __forceinline__ float clip01_nan(float s) {
+    float r;
+    asm("min.NaN.f32 %0, %1, 0f3F800000;\n\tmax.NaN.f32 %0, %0, 0f00000000;" : "=f"(r) : "f"(s));
+    return r;
+}
+
+__device__ __forceinline__ float srgb_encode_h(float c) {
+    float s = c > CT_THR_ENC_F ? fmaf(1.055f, ex2_approx(0.41666666f * lg2_approx(c)), -0.055f) : 12.92f * c;
+    return clip01_nan(s);
+}
+
+// Statistics pass: one pixel as w = (fy - 66/116, fx - fy, fy - fz), i.e. Lab = (50 + 116 w0,
+// 500 w1, 200 w2); the caller scales the SUMS instead of every pixel.  FMA_SEEDS of the three
+// cube roots avoid the XU pipe.
+#define CT_LAB_W0_SHIFT (66.0f / 116.0f)
+template <int FMA_SEEDS>
+__device__ __forceinline__ void rgb2labw_h(const float (&rgb)[3], float (&w)[3]) {
+    const float l0 = srgb_decode_h<true>(rgb[0]), l1 = srgb_decode_h<true>(rgb[1]), l2 = srgb_decode_h<true>(rgb[2]);
+    const float fx = lab_f_h<(FMA_SEEDS > 1), false>(CT_XYZ_ROW0(float, l0, l1, l2));
+    const float fy = lab_f_h<(FMA_SEEDS > 0), false>(CT_XYZ_ROW1(float, l0, l1, l2));
+    const float fz = lab_f_h<(FMA_SEEDS > 2), false>(CT_XYZ_ROW2(float, l0, l1, l2));
+    w[0] = fy - CT_LAB_W0_SHIFT;
+    w[1] = fx - fy;
+    w[2] = fy - fz;
+}
+
+// Per-pair constants of the fused Lab affine, folded so that the 116/500/200 scalings cancel:
+//   fy' = sL fy + cL,  fx' = fy' + sa (fx - fy) + ca,  fz' = fy' - sb (fy - fz) - cb
+struct ReinhardFold {
+    float sL, cL, sa, ca, sb, cb;
+};
+// xf: the CT_XFORM_DOUBLES block of the pair (scales at 0,4,8; mean_t at 9..11; mean_r at 12..14)
+__device__ __forceinline__ ReinhardFold fold_reinhard(const double *xf) {
+    ReinhardFold k;
+    k.sL = (float)xf[0];
+    k.cL = (float)((xf[12] - (16.0 + xf[9]) * xf[0] + 16.0) / 116.0);
+    k.sa = (float)xf[4];
+    k.ca = (float)((xf[13] - xf[10] * xf[4]) / 500.0);
+    k.sb = (float)xf[8];
+    k.cb = (float)((xf[14] - xf[11] * xf[8]) / 200.0);
+    return k;
+}
+
+// rgb (float) -> Reinhard-transferred rgb (float), clipped to [0,1]  (linear.py:25-40 fused)
+template <int FMA_SEEDS>
+__device__ __forceinline__ void reinhard_pixel_h(const ReinhardFold &k, const float (&v)[3], float (&out)[3]) {
+    const float l0 = srgb_decode_h<false>(v[0]), l1 = srgb_decode_h<false>(v[1]), l2 = srgb_decode_h<false>(v[2]);
+    const float fx = lab_f_h<(FMA_SEEDS > 1), true>(CT_XYZ_ROW0(float, l0, l1, l2));
+    const float fy = lab_f_h<(FMA_SEEDS > 0), true>(CT_XYZ_ROW1(float, l0, l1, l2));
+    const float fz = lab_f_h<(FMA_SEEDS > 2), true>(CT_XYZ_ROW2(float, l0, l1, l2));
+    const float gy = fmaf(k.sL, fy, k.cL);
+    const float gx = fmaf(k.sa, fx - fy, k.ca) + gy;
+    float gz = gy - fmaf(k.sb, fy - fz, k.cb);
+    asm("max.NaN.f32 %0, %0, 0f00000000;" : "+f"(gz));  // skimage zeroes invalid z (and warns)
+    const float X = finv_h(gx), Y = finv_h(gy), Z = finv_h(gz);
+    out[0] = srgb_encode_h(fmaf(-0.5428213080224701f, Z, fmaf(-1.5371515162713183f, Y, 3.079980302271805f * X)));
+    out[1] = srgb_encode_h(fmaf(0.045247339514465995f, Z, fmaf(1.8759900014898907f, Y, -0.9212477523232383f * X)));
+    out[2] = srgb_encode_h(fmaf(1.1512320119619401f, Z, fmaf(-0.20404133836651123f, Y, 0.05289046109881184f * X)));
 }
 
 }  // namespace lab

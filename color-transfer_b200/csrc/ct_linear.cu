@@ -26,32 +26,53 @@ struct MomentsArgs {
     int *status;       // [B]
 };
 
-template <bool LAB>
-__device__ __forceinline__ void accumulate(const double (&rgb)[3], const float (&rgbf)[3], double (&acc)[9]) {
-    double v[3];
-    if (LAB) {
-        // statistics only: the fp32 Lab chain (ct_lab.cuh), accumulated in fp64
-        float labf[3];
-        lab::rgb2lab_f32(rgbf, labf);
-        v[0] = (double)(labf[0] - 50.0f);
-        v[1] = (double)labf[1];
-        v[2] = (double)labf[2];
-    } else {
-        v[0] = rgb[0] - 0.5;
-        v[1] = rgb[1] - 0.5;
-        v[2] = rgb[2] - 0.5;
+// Cube-root seeds of the Lab kernels taken from the FMA pipe instead of MUFU (0..3 of the three
+// per pixel): with 0 both kernels are bound by the XU pipe, with 3 by instruction issue.
+#ifndef CT_STATS_FMA_SEEDS
+#define CT_STATS_FMA_SEEDS 2
+#endif
+#ifndef CT_REINHARD_FMA_SEEDS
+#define CT_REINHARD_FMA_SEEDS 1
+#endif
+#ifndef CT_LAB_CTAS_PER_SM   // resident CTAs per SM the Lab kernels are compiled for (register cap)
+#define CT_LAB_CTAS_PER_SM 4
+#endif
+
+__device__ __forceinline__ void accumulate_rgb(const double (&rgb)[3], double (&acc)[9]) {
+    const double v0 = rgb[0] - 0.5, v1 = rgb[1] - 0.5, v2 = rgb[2] - 0.5;
+    acc[0] += v0;
+    acc[1] += v1;
+    acc[2] += v2;
+    acc[3] = fma(v0, v0, acc[3]);
+    acc[4] = fma(v0, v1, acc[4]);
+    acc[5] = fma(v0, v2, acc[5]);
+    acc[6] = fma(v1, v1, acc[6]);
+    acc[7] = fma(v1, v2, acc[7]);
+    acc[8] = fma(v2, v2, acc[8]);
+}
+
+// Lab statistics (Reinhard needs only per-channel mean and variance): the fp32 Lab chain of
+// ct_lab.cuh, summed in fp32 over the N pixels a thread holds and only then folded into the
+// fp64 accumulators - 6 F2F conversions (XU pipe) per group instead of per pixel.
+template <int N>
+__device__ __forceinline__ void accumulate_lab(const float (&rgbf)[N][3], double (&acc)[9]) {
+    float s[3] = {0.0f, 0.0f, 0.0f}, q[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        float labf[3];  // (L - 50) / 116, a / 500, b / 200: scaled back when the sums are combined
+        lab::rgb2labw_h<CT_STATS_FMA_SEEDS>(rgbf[i], labf);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            s[c] += labf[c];
+            q[c] = fmaf(labf[c], labf[c], q[c]);
+        }
     }
-    acc[0] += v[0];
-    acc[1] += v[1];
-    acc[2] += v[2];
-    acc[3] = fma(v[0], v[0], acc[3]);
-    acc[6] = fma(v[1], v[1], acc[6]);
-    acc[8] = fma(v[2], v[2], acc[8]);
-    if (!LAB) {  // Reinhard needs only the per-channel variances
-        acc[4] = fma(v[0], v[1], acc[4]);
-        acc[5] = fma(v[0], v[2], acc[5]);
-        acc[7] = fma(v[1], v[2], acc[7]);
-    }
+    acc[0] += (double)s[0];
+    acc[1] += (double)s[1];
+    acc[2] += (double)s[2];
+    acc[3] += (double)q[0];
+    acc[6] += (double)q[1];
+    acc[8] += (double)q[2];
 }
 
 template <typename IO, bool VEC, bool LAB>
@@ -61,25 +82,48 @@ __device__ __forceinline__ void moments_image(const Img &im, int64_t pair, doubl
     constexpr int G = IO::G;
     const int64_t ngroups = im.npix / G;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += stride) {
-        const typename IO::Raw raw = IO::template load_raw<VEC>(base, im.plane_stride, (int)g);
-        double x[G][3];
-        float xf[G][3];
-        if (LAB) IO::unpack_f(raw, xf); else IO::unpack(raw, x);
+    int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (LAB) {
+        if (g < ngroups) {
+            // compute-heavy pass: the next group's three vectors are in flight while this one is worked on
+            typename IO::Raw raw = IO::template load_raw<VEC>(base, im.plane_stride, (int)g);
+            for (;;) {
+                g += stride;
+                const bool more = g < ngroups;
+                typename IO::Raw next;
+                if (more) next = IO::template load_raw<VEC>(base, im.plane_stride, (int)g);
+                float xf[G][3];
+                IO::unpack_f(raw, xf);
+                accumulate_lab<G>(xf, acc);
+                if (!more) break;
+                raw = next;
+            }
+        }
+    } else {
+        for (; g < ngroups; g += stride) {
+            const typename IO::Raw raw = IO::template load_raw<VEC>(base, im.plane_stride, (int)g);
+            double x[G][3];
+            IO::unpack(raw, x);
 #pragma unroll
-        for (int i = 0; i < G; ++i) accumulate<LAB>(x[i], xf[i], acc);
+            for (int i = 0; i < G; ++i) accumulate_rgb(x[i], acc);
+        }
     }
     if (blockIdx.x == 0) {
         for (int64_t p = ngroups * G + threadIdx.x; p < im.npix; p += kThreads) {
             double x[3];
             IO::load1(base, im.plane_stride, p, x);
-            const float xf[3] = {(float)x[0], (float)x[1], (float)x[2]};
-            accumulate<LAB>(x, xf, acc);
+            if (LAB) {
+                const float xf[1][3] = {{(float)x[0], (float)x[1], (float)x[2]}};
+                accumulate_lab<1>(xf, acc);
+            } else {
+                accumulate_rgb(x, acc);
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 3) moments_kernel(MomentsArgs a) {
+template <bool LAB>
+__global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_CTAS_PER_SM : 3) moments_kernel(MomentsArgs a) {
     const int z = blockIdx.z;
     const int64_t pair = blockIdx.y;
     double acc[9];
@@ -88,18 +132,10 @@ __global__ void __launch_bounds__(kThreads, 3) moments_kernel(MomentsArgs a) {
 
     const Img im = a.img[z];
     const int sel = a.kind[z] * 2 + a.vec[z];
-    if (a.lab) {
-        switch (sel) {
-#define CT_CASE(ID, T, L, V) case ID: moments_image<PixelIO<T, L>, V, true>(im, pair, acc); break;
-            CT_FOR_EACH_SRC(CT_CASE)
+    switch (sel) {
+#define CT_CASE(ID, T, L, V) case ID: moments_image<PixelIO<T, L>, V, LAB>(im, pair, acc); break;
+        CT_FOR_EACH_SRC(CT_CASE)
 #undef CT_CASE
-        }
-    } else {
-        switch (sel) {
-#define CT_CASE(ID, T, L, V) case ID: moments_image<PixelIO<T, L>, V, false>(im, pair, acc); break;
-            CT_FOR_EACH_SRC(CT_CASE)
-#undef CT_CASE
-        }
     }
 
     __shared__ double red[kWarps][9];
@@ -136,6 +172,10 @@ __global__ void __launch_bounds__(kThreads, 3) moments_kernel(MomentsArgs a) {
         const double *p = a.partials + ((int64_t)pair * a.nimg + img) * nblk * 9 + k;
         double s = 0.0;
         for (int64_t b = 0; b < nblk; ++b) s += __ldcg(p + b * 9);
+        if (LAB) {  // the Lab pass sums w = ((L - 50) / 116, a / 500, b / 200) and their squares
+            const double f = (k == 0 || k == 3) ? 116.0 : (k == 1 || k == 6) ? 500.0 : 200.0;
+            s *= k < 3 ? f : f * f;
+        }
         total[img][1 + k] = s;
         if (k == 0) total[img][0] = (double)a.img[img].npix;
     }
@@ -191,17 +231,24 @@ __device__ __forceinline__ void apply_pixel(const double *xf, const float *xff, 
     }
 }
 
+template <typename A, typename B> struct same_t { static constexpr bool value = false; };
+template <typename A> struct same_t<A, A> { static constexpr bool value = true; };
+
 template <typename SIO, typename DIO, bool VEC, bool LAB>
-__global__ void __launch_bounds__(kThreads, LAB ? 4 : 3) apply_kernel(ApplyArgs a) {
+__global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_CTAS_PER_SM : 3) apply_kernel(ApplyArgs a) {
     using TS = typename SIO::elem_t;
     using TD = typename DIO::elem_t;
+    // float32 in and out (Reinhard keeps the input dtype, linear.py:25-40): the hybrid chain
+    constexpr bool HYB = LAB && same_t<TS, float>::value && same_t<TD, float>::value;
     const int64_t pair = blockIdx.y;
     __shared__ double xf[CT_XFORM_DOUBLES];
     __shared__ float xff[CT_XFORM_DOUBLES];
+    __shared__ lab::ReinhardFold fold;
     if (threadIdx.x < CT_XFORM_DOUBLES) {
         xf[threadIdx.x] = a.xform[pair * CT_XFORM_DOUBLES + threadIdx.x];
         xff[threadIdx.x] = (float)xf[threadIdx.x];
     }
+    if (HYB && threadIdx.x == 32) fold = lab::fold_reinhard(a.xform + pair * CT_XFORM_DOUBLES);
     __syncthreads();
     const TS *src = reinterpret_cast<const TS *>(a.src.data) + pair * a.src.image_stride;
     TD *dst = reinterpret_cast<TD *>(a.dst.data) + pair * a.dst.image_stride;
@@ -210,21 +257,35 @@ __global__ void __launch_bounds__(kThreads, LAB ? 4 : 3) apply_kernel(ApplyArgs 
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += stride) {
         const typename SIO::Raw raw = SIO::template load_raw<VEC>(src, a.src.plane_stride, (int)g);
-        double x[G][3], y[G][3];
-        float xs[G][3];
-        SIO::unpack(raw, x);
-        if (LAB) SIO::unpack_f(raw, xs);
+        if (HYB) {
+            float xs[G][3], ys[G][3];
+            SIO::unpack_f(raw, xs);
 #pragma unroll
-        for (int i = 0; i < G; ++i) apply_pixel<LAB>(xf, xff, x[i], xs[i], y[i]);
-        DIO::template store<VEC, G>(dst, a.dst.plane_stride, g * G, y);
+            for (int i = 0; i < G; ++i) lab::reinhard_pixel_h<CT_REINHARD_FMA_SEEDS>(fold, xs[i], ys[i]);
+            DIO::template store<VEC, G>(dst, a.dst.plane_stride, g * G, ys);
+        } else {
+            double x[G][3], y[G][3];
+            float xs[G][3];
+            SIO::unpack(raw, x);
+            if (LAB) SIO::unpack_f(raw, xs);
+#pragma unroll
+            for (int i = 0; i < G; ++i) apply_pixel<LAB>(xf, xff, x[i], xs[i], y[i]);
+            DIO::template store<VEC, G>(dst, a.dst.plane_stride, g * G, y);
+        }
     }
     if (blockIdx.x == 0) {
         for (int64_t p = ngroups * G + threadIdx.x; p < a.src.npix; p += kThreads) {
             double x[3], y[3];
             SIO::load1(src, a.src.plane_stride, p, x);
             const float xs[3] = {(float)x[0], (float)x[1], (float)x[2]};
-            apply_pixel<LAB>(xf, xff, x, xs, y);
-            DIO::store1(dst, a.dst.plane_stride, p, y);
+            if (HYB) {
+                float ys[3];
+                lab::reinhard_pixel_h<CT_REINHARD_FMA_SEEDS>(fold, xs, ys);
+                DIO::store1(dst, a.dst.plane_stride, p, ys);
+            } else {
+                apply_pixel<LAB>(xf, xff, x, xs, y);
+                DIO::store1(dst, a.dst.plane_stride, p, y);
+            }
         }
     }
 }
@@ -254,7 +315,7 @@ int launch_moments(ct_context *h, const ct_batch *a, const ct_batch *b, int lab,
     if (b && b->npix > npix_max) npix_max = b->npix;
     // a single pair: one resident wave (3 CTAs/SM) keeps the fixed-order combine short; batches of
     // small images: more, smaller CTAs balance better
-    const int nblk = blocks_for(h, npix_max, 2, (int64_t)B * nimg, B == 1 ? 3 : 8);
+    const int nblk = blocks_for(h, npix_max, 2, (int64_t)B * nimg, B == 1 ? (lab ? 4 : 3) : 8);
     CT_TRY(ensure_partials(h, (size_t)B * nimg * nblk * 9));
     CT_TRY(ensure_scratch(h, B));
     MomentsArgs m{};
@@ -274,7 +335,8 @@ int launch_moments(ct_context *h, const ct_batch *a, const ct_batch *b, int lab,
     m.method = (b && xform) ? method : -1;
     m.xform = xform;
     m.status = status;
-    moments_kernel<<<dim3(nblk, B, nimg), kThreads, 0, h->stream>>>(m);
+    if (lab) moments_kernel<true><<<dim3(nblk, B, nimg), kThreads, 0, h->stream>>>(m);
+    else moments_kernel<false><<<dim3(nblk, B, nimg), kThreads, 0, h->stream>>>(m);
     h->launches++;
     CT_CUDA(h, cudaGetLastError());
     return CT_OK;
