@@ -39,6 +39,19 @@ template <typename T> struct Vec;
 template <> struct Vec<float> { using type = float4; static constexpr int G = 4; };
 template <> struct Vec<double> { using type = double2; static constexpr int G = 2; };
 
+// output vectors are written once and not read again by the same kernel
+#ifndef CT_STORE_CS
+#define CT_STORE_CS 0
+#endif
+template <typename V>
+__device__ __forceinline__ void st_vec(V *p, const V &v) {
+#if CT_STORE_CS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 template <typename T, int LAYOUT>
 struct PixelIO {
     static constexpr int G = Vec<T>::G;
@@ -141,7 +154,7 @@ struct PixelIO {
                 for (int c = 0; c < 3; ++c) raw[3 * i + c] = (T)x[i][c];
             V *v = reinterpret_cast<V *>(img + 3 * p0);
 #pragma unroll
-            for (int k = 0; k < 3 * NV; ++k) v[k] = *reinterpret_cast<V *>(&raw[k * G]);
+            for (int k = 0; k < 3 * NV; ++k) st_vec(v + k, *reinterpret_cast<V *>(&raw[k * G]));
         } else {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -150,7 +163,7 @@ struct PixelIO {
                 for (int i = 0; i < GS; ++i) raw[i] = (T)x[i][c];
                 V *v = reinterpret_cast<V *>(img + c * plane + p0);
 #pragma unroll
-                for (int k = 0; k < NV; ++k) v[k] = *reinterpret_cast<V *>(&raw[k * G]);
+                for (int k = 0; k < NV; ++k) st_vec(v + k, *reinterpret_cast<V *>(&raw[k * G]));
             }
         }
     }

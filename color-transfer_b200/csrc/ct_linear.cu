@@ -34,6 +34,15 @@ struct MomentsArgs {
 #ifndef CT_REINHARD_FMA_SEEDS
 #define CT_REINHARD_FMA_SEEDS 1
 #endif
+// Minimum waves of a batched remap launch.  CTAs are scheduled pair by pair (blockIdx.y), so more,
+// smaller CTAs per pair keep fewer images open at once: the write-heavy plain remap (12 B in,
+// 24 B out per pixel) gains 5 % from 4 -> 12+ waves, the compute-heavy Lab remap prefers 4-8.
+#ifndef CT_APPLY_MIN_WAVES
+#define CT_APPLY_MIN_WAVES 12
+#endif
+#ifndef CT_APPLY_LAB_MIN_WAVES
+#define CT_APPLY_LAB_MIN_WAVES 4
+#endif
 #ifndef CT_LAB_CTAS_PER_SM   // resident CTAs per SM the Lab kernels are compiled for (register cap)
 #define CT_LAB_CTAS_PER_SM 4
 #endif
@@ -293,12 +302,30 @@ __global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_CTAS_PER_SM : 3) apply_
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-static int blocks_for(const ct_context *h, int64_t npix, int group, int64_t units, int per_sm) {
-    const int64_t want = (npix / group + kThreads - 1) / kThreads;
-    int64_t cap = ((int64_t)h->sm_count * per_sm) / (units > 0 ? units : 1);
-    if (cap < 1) cap = 1;
-    int64_t n = want < cap ? want : cap;
-    return (int)(n < 1 ? 1 : n);
+// CTAs per image for a launch of `units` images that keeps `ctas_per_sm` CTAs resident per SM
+// (the kernel's __launch_bounds__): every CTA does the same work, so the grid is sized to fill
+// WHOLE waves - a 5.3-wave grid runs as long as a 6-wave one.  Picks the smallest wave count whose
+// last wave is at least 97 % full (or the fullest of eight candidates), starting at `min_waves`:
+// the remap kernels run best with >= 4 waves, the moments pass with few (short combine).
+static int blocks_for(const ct_context *h, int64_t npix, int group, int64_t units, int ctas_per_sm, int min_waves) {
+    int64_t want = (npix / group + kThreads - 1) / kThreads;
+    if (want < 1) want = 1;
+    if (units < 1) units = 1;
+    const int64_t resident = (int64_t)h->sm_count * ctas_per_sm;
+    int64_t best = 1;
+    double best_fill = 0.0;
+    for (int waves = min_waves; waves <= min_waves + 7; ++waves) {
+        int64_t n = resident * waves / units;
+        if (n < 1) continue;
+        if (n >= want) return (int)want;   // small images: one CTA per kThreads groups
+        const double fill = (double)(n * units) / (double)(resident * waves);
+        if (fill > best_fill) {
+            best_fill = fill;
+            best = n;
+        }
+        if (fill >= 0.97) break;
+    }
+    return (int)best;
 }
 
 int launch_moments(ct_context *h, const ct_batch *a, const ct_batch *b, int lab, double *sums,
@@ -313,9 +340,8 @@ int launch_moments(ct_context *h, const ct_batch *a, const ct_batch *b, int lab,
     const int B = a->count;
     int64_t npix_max = a->npix;
     if (b && b->npix > npix_max) npix_max = b->npix;
-    // a single pair: one resident wave (3 CTAs/SM) keeps the fixed-order combine short; batches of
-    // small images: more, smaller CTAs balance better
-    const int nblk = blocks_for(h, npix_max, 2, (int64_t)B * nimg, B == 1 ? (lab ? 4 : 3) : 8);
+    // a single pair gets exactly one resident wave (short fixed-order combine); batches whole waves
+    const int nblk = blocks_for(h, npix_max, 2, (int64_t)B * nimg, lab ? CT_LAB_CTAS_PER_SM : 3, 1);
     CT_TRY(ensure_partials(h, (size_t)B * nimg * nblk * 9));
     CT_TRY(ensure_scratch(h, B));
     MomentsArgs m{};
@@ -373,7 +399,8 @@ int launch_apply(ct_context *h, int method, const ct_batch *target, const double
     if (out->layout != CT_HWC) return fail(h, CT_E_UNSUPPORTED, "linear output must be CT_HWC");
     const bool vec = vec_ok(target) && vec_ok(out);
     const int group = target->dtype == CT_F32 ? 4 : 2;
-    const int nblk = blocks_for(h, target->npix, group, target->count, target->count == 1 ? (method == CT_REINHARD ? 4 : 3) : 16);
+    const int nblk = blocks_for(h, target->npix, group, target->count, method == CT_REINHARD ? CT_LAB_CTAS_PER_SM : 3,
+                                target->count == 1 ? 1 : (method == CT_REINHARD ? CT_APPLY_LAB_MIN_WAVES : CT_APPLY_MIN_WAVES));
     const dim3 grid(nblk, target->count);
     ApplyArgs a{img_of(target), imgout_of(out), xform};
     const bool labm = method == CT_REINHARD;
