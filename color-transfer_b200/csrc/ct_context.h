@@ -37,6 +37,13 @@ struct ct_context {
 
     // host pipeline
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+
+    // batched linear transfers: chunks of pairs alternate between two side streams so that the
+    // serial tail of one chunk's statistics pass overlaps the next chunk's streaming
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+    int ticket_base = 0;        // first ticket and first partials double a moments launch may use
+    size_t partials_base = 0;   // (one region per side stream)
 };
 
 namespace ct {

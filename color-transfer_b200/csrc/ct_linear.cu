@@ -66,14 +66,14 @@ __device__ __forceinline__ void accumulate_rgb(const double (&rgb)[3], double (&
 template <int N>
 __device__ __forceinline__ void accumulate_lab(const float (&rgbf)[N][3], double (&acc)[9]) {
     float s[3] = {0.0f, 0.0f, 0.0f}, q[3] = {0.0f, 0.0f, 0.0f};
+    float w[N][3];  // (L - 50) / 116, a / 500, b / 200: scaled back when the sums are combined
+    lab::rgb2labw_group<N, CT_STATS_FMA_SEEDS>(rgbf, w);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        float labf[3];  // (L - 50) / 116, a / 500, b / 200: scaled back when the sums are combined
-        lab::rgb2labw_h<CT_STATS_FMA_SEEDS>(rgbf[i], labf);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            s[c] += labf[c];
-            q[c] = fmaf(labf[c], labf[c], q[c]);
+            s[c] += w[i][c];
+            q[c] = fmaf(w[i][c], w[i][c], q[c]);
         }
     }
     acc[0] += (double)s[0];
@@ -175,18 +175,23 @@ __global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_CTAS_PER_SM : 3) moment
     if (!is_last) return;
     __threadfence();
 
-    // fixed-order combine: thread (img, k) walks the partials of its image in block order
-    if (threadIdx.x < 9 * a.nimg) {
-        const int img = threadIdx.x / 9, k = threadIdx.x % 9;
+    // fixed-order combine, one warp per quantity (img, k): lane l adds the partials of blocks
+    // l, l+32, ... in that order, then a fixed shuffle tree - deterministic for a given grid, and
+    // ~30x shorter than one thread walking all blocks (this tail is most of a small launch).
+    for (int q = warp; q < 9 * a.nimg; q += kWarps) {
+        const int img = q / 9, k = q % 9;
         const double *p = a.partials + ((int64_t)pair * a.nimg + img) * nblk * 9 + k;
         double s = 0.0;
-        for (int64_t b = 0; b < nblk; ++b) s += __ldcg(p + b * 9);
-        if (LAB) {  // the Lab pass sums w = ((L - 50) / 116, a / 500, b / 200) and their squares
-            const double f = (k == 0 || k == 3) ? 116.0 : (k == 1 || k == 6) ? 500.0 : 200.0;
-            s *= k < 3 ? f : f * f;
+        for (int64_t b = lane; b < nblk; b += 32) s += __ldcg(p + b * 9);
+        s = warp_sum(s);
+        if (lane == 0) {
+            if (LAB) {  // the Lab pass sums w = ((L - 50) / 116, a / 500, b / 200) and their squares
+                const double f = (k == 0 || k == 3) ? 116.0 : (k == 1 || k == 6) ? 500.0 : 200.0;
+                s *= k < 3 ? f : f * f;
+            }
+            total[img][1 + k] = s;
+            if (k == 0) total[img][0] = (double)a.img[img].npix;
         }
-        total[img][1 + k] = s;
-        if (k == 0) total[img][0] = (double)a.img[img].npix;
     }
     __syncthreads();
     if (threadIdx.x < 10 * a.nimg) {
@@ -269,8 +274,7 @@ __global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_CTAS_PER_SM : 3) apply_
         if (HYB) {
             float xs[G][3], ys[G][3];
             SIO::unpack_f(raw, xs);
-#pragma unroll
-            for (int i = 0; i < G; ++i) lab::reinhard_pixel_h<CT_REINHARD_FMA_SEEDS>(fold, xs[i], ys[i]);
+            lab::reinhard_group_h<G, CT_REINHARD_FMA_SEEDS>(fold, xs, ys);
             DIO::template store<VEC, G>(dst, a.dst.plane_stride, g * G, ys);
         } else {
             double x[G][3], y[G][3];
@@ -288,9 +292,10 @@ __global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_CTAS_PER_SM : 3) apply_
             SIO::load1(src, a.src.plane_stride, p, x);
             const float xs[3] = {(float)x[0], (float)x[1], (float)x[2]};
             if (HYB) {
-                float ys[3];
-                lab::reinhard_pixel_h<CT_REINHARD_FMA_SEEDS>(fold, xs, ys);
-                DIO::store1(dst, a.dst.plane_stride, p, ys);
+                const float x1[1][3] = {{xs[0], xs[1], xs[2]}};
+                float y1[1][3];
+                lab::reinhard_group_h<1, CT_REINHARD_FMA_SEEDS>(fold, x1, y1);
+                DIO::store1(dst, a.dst.plane_stride, p, y1[0]);
             } else {
                 apply_pixel<LAB>(xf, xff, x, xs, y);
                 DIO::store1(dst, a.dst.plane_stride, p, y);
@@ -342,8 +347,9 @@ int launch_moments(ct_context *h, const ct_batch *a, const ct_batch *b, int lab,
     if (b && b->npix > npix_max) npix_max = b->npix;
     // a single pair gets exactly one resident wave (short fixed-order combine); batches whole waves
     const int nblk = blocks_for(h, npix_max, 2, (int64_t)B * nimg, lab ? CT_LAB_CTAS_PER_SM : 3, 1);
-    CT_TRY(ensure_partials(h, (size_t)B * nimg * nblk * 9));
-    CT_TRY(ensure_scratch(h, B));
+    // (a chunked batch pre-sizes both buffers: growing them here would free memory in use)
+    CT_TRY(ensure_partials(h, h->partials_base + (size_t)B * nimg * nblk * 9));
+    CT_TRY(ensure_scratch(h, h->ticket_base + B));
     MomentsArgs m{};
     m.img[0] = img_of(a);
     m.kind[0] = src_kind(a);
@@ -355,8 +361,8 @@ int launch_moments(ct_context *h, const ct_batch *a, const ct_batch *b, int lab,
     }
     m.nimg = nimg;
     m.lab = lab;
-    m.partials = h->partials;
-    m.tickets = h->tickets;
+    m.partials = h->partials + h->partials_base;
+    m.tickets = h->tickets + h->ticket_base;
     m.sums = sums;
     m.method = (b && xform) ? method : -1;
     m.xform = xform;
