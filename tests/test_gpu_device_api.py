@@ -168,3 +168,43 @@ def test_uint8_frame_io(mods, as_float32):
     # the float path on the decoded frames gives the same bytes
     again = quantise(batch.idt_frames(tf, rf, rotations=rot))
     assert np.array_equal(again, batch.idt_frames_u8(t8, r8, rotations=rot, as_float32=as_float32))
+
+
+def test_large_reinhard_batch_runs_chunked_on_two_streams(mods):
+    """Batches of >= 32 pairs go through the two-stream chunked driver (ct_linear_transfer): the
+    result must match the same pairs transferred one call at a time and the oracle."""
+    torch, _cabi, batch, device, sharded, synth, oracle = mods
+    B, H, W = 37, 40, 52                                   # odd count: the last chunk is shorter
+    t, r = _stack(B, H, W, np.float32, seed=300)
+    dt, dr = torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda()
+    for code, fn, tol in ((_cabi.CT_REINHARD, oracle.color_transfer_between_images, 1e-4),
+                          (_cabi.CT_MKL_MK, oracle.monge_kantorovitch_color_transfer, 1e-9)):
+        whole = device.linear_transfer(code, dt, dr).cpu().numpy()
+        for b in (0, 9, 10, 18, 27, 36):
+            single = device.linear_transfer(code, dt[b:b + 1], dr[b:b + 1]).cpu().numpy()[0]
+            assert np.max(np.abs(whole[b].astype(np.float64) - single)) <= 1e-6
+            ref = fn(t[b].astype(np.float64), r[b].astype(np.float64))
+            assert np.max(np.abs(whole[b] - ref)) <= tol
+    torch.cuda.synchronize()
+
+
+def test_reinhard_float32_toes_and_nan(mods):
+    """float32 Reinhard: images that live entirely in the linear toes of the gamma / Lab curves
+    (the patched rare branches of ct_lab.cuh), and NaN propagation like numpy (a NaN pixel turns the
+    statistics, hence every output, into NaN)."""
+    torch, _cabi, batch, device, sharded, synth, oracle = mods
+    rng = np.random.default_rng(5)
+    dark_t = (rng.integers(0, 12, (64, 80, 3)) / 255.0).astype(np.float32)      # all below 0.04045
+    dark_r = (rng.integers(0, 30, (64, 80, 3)) / 255.0).astype(np.float32)
+    mixed_t = dark_t.copy()
+    mixed_t[::7, ::5] = (rng.integers(0, 256, mixed_t[::7, ::5].shape) / 255.0).astype(np.float32)
+    for t, r in ((dark_t, dark_r), (mixed_t, dark_r), (dark_r, mixed_t)):
+        out = device.linear_transfer(_cabi.CT_REINHARD, torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda()).cpu().numpy()
+        ref = oracle.color_transfer_between_images(t.astype(np.float64), r.astype(np.float64))
+        assert out.dtype == np.float32 and out.min() >= 0.0 and out.max() <= 1.0
+        assert np.max(np.abs(out - ref)) <= 1e-4
+    bad = mixed_t.copy()
+    bad[3, 4, 1] = np.nan
+    for t, r in ((bad, dark_r), (dark_r, bad)):
+        out = device.linear_transfer(_cabi.CT_REINHARD, torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda()).cpu().numpy()
+        assert np.isnan(out).all()
