@@ -37,6 +37,9 @@ struct ct_context {
 
     // host pipeline
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    // pinned bounce buffers for pageable caller memory (ct_host_copy.h): 2 chunks per direction
+    unsigned char *bounce[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    cudaEvent_t bounce_done[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
 
     // batched linear transfers: chunks of pairs alternate between two side streams so that the
     // serial tail of one chunk's statistics pass overlaps the next chunk's streaming
