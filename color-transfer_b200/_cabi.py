@@ -83,6 +83,9 @@ SIGNATURES = {
                                        ctypes.POINTER(IdtTrace), _P]),
     "ct_idt_transfer_host": (ctypes.c_int, [_P, _BP, _BP, _BP, _P, ctypes.c_int32, ctypes.c_int32,
                                             ctypes.POINTER(IdtTrace)]),
+    "ct_icid": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                               ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]),
+    "ct_psnr": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.c_int64, ctypes.POINTER(ctypes.c_double)]),
 }
 
 _lib = None

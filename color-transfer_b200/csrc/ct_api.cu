@@ -350,6 +350,30 @@ int ct_linear_transfer(ct_handle h, int method, const ct_batch *target, const ct
     return rc;
 }
 
+// ------------------------------------------------------------------ quality metrics
+static int metric_result(ct_context *h, double *result) {
+    CT_CUDA(h, cudaMemcpyAsync(result, h->sums, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CT_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CT_OK;
+}
+
+int ct_icid(ct_handle h, const float *img1, const float *img2, int32_t count, int32_t height, int32_t width,
+            int32_t intent, int32_t omit_maps67, int32_t downsampling, double *result) {
+    CT_ENTER(h);
+    if (!result) return fail(h, CT_E_INVALID, "result is NULL");
+    CT_TRY(ensure_scratch(h, 1));
+    CT_TRY(launch_icid(h, img1, img2, count, height, width, intent, omit_maps67, downsampling, h->sums));
+    return metric_result(h, result);
+}
+
+int ct_psnr(ct_handle h, const float *x, const float *y, int32_t count, int64_t elems_per_image, double *result) {
+    CT_ENTER(h);
+    if (!result) return fail(h, CT_E_INVALID, "result is NULL");
+    CT_TRY(ensure_scratch(h, 1));
+    CT_TRY(launch_psnr(h, x, y, count, elems_per_image, h->sums));
+    return metric_result(h, result);
+}
+
 }  // extern "C"
 
 // Host pipeline shared by the two *_host entry points: per pair H2D on copy_in, kernels on the

@@ -207,6 +207,23 @@ int ct_idt_transfer_host_u8(ct_handle h, const uint8_t *target, const uint8_t *r
                             int32_t count, int64_t npix_target, int64_t npix_reference,
                             int32_t as_float32, const double *rotations, int32_t bins, int32_t n_iter);
 
+/* ------------------------------------------------------------------ quality metrics
+ * The step after the hot path in the reference's test loop (ref: methods/__init__.py:32-40), on
+ * planar float32 image batches [count,3,height,width] in DEVICE memory.  Both calls are ordered on
+ * the handle's stream, write one double to `result` (HOST memory) and return after it is there.
+ *
+ * ct_icid replaces ref: utils/icid.py:28 `icid(img1, img2, intent, omit_maps67, downsampling)`:
+ * intent 0 = "perceptual", 1 = "hue-preserving", 2 = "chromatic" (anything else: CT_E_INVALID, the
+ * reference's ValueError); the result is 1 - mean over batch and pixels of the map product.
+ * ct_psnr replaces piq.psnr(x, y) with its defaults (ref: methods/__init__.py:35): the mean over
+ * the batch of -10 log10(mse + 1e-8), data_range 1. */
+#define CT_ICID_PERCEPTUAL 0
+#define CT_ICID_HUE_PRESERVING 1
+#define CT_ICID_CHROMATIC 2
+int ct_icid(ct_handle h, const float *img1, const float *img2, int32_t count, int32_t height, int32_t width,
+            int32_t intent, int32_t omit_maps67, int32_t downsampling, double *result);
+int ct_psnr(ct_handle h, const float *x, const float *y, int32_t count, int64_t elems_per_image, double *result);
+
 #ifdef __cplusplus
 }
 #endif

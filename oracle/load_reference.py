@@ -70,3 +70,39 @@ def linear():
 def iterative():
     """The reference's methods/iterative.py as a module object."""
     return _load("_ct_reference_iterative", os.path.join("methods", "iterative.py"))
+
+
+def icid():
+    """The reference's utils/icid.py ``icid`` function.  kornia is not installed, so
+    ``kornia.color.rgb_to_lab`` is stubbed by a torch restatement of kornia's published
+    algorithm (the same constants as scikit-image's rgb2lab); torch and torchvision are real."""
+    import torch
+
+    def rgb_to_lab(image):
+        lin = torch.where(image > 0.04045, torch.pow((image + 0.055) / 1.055, 2.4), image / 12.92)
+        r, g, b = lin[..., 0, :, :], lin[..., 1, :, :], lin[..., 2, :, :]
+        x = (0.412453 * r + 0.357580 * g + 0.180423 * b) / 0.95047
+        y = (0.212671 * r + 0.715160 * g + 0.072169 * b) / 1.0
+        z = (0.019334 * r + 0.119193 * g + 0.950227 * b) / 1.08883
+        xyz = torch.stack([x, y, z], dim=-3)
+        f = torch.where(xyz > 0.008856, torch.pow(xyz.clamp(min=0.008856), 1.0 / 3.0), 7.787 * xyz + 4.0 / 29.0)
+        fx, fy, fz = f[..., 0, :, :], f[..., 1, :, :], f[..., 2, :, :]
+        return torch.stack([116.0 * fy - 16.0, 500.0 * (fx - fy), 200.0 * (fy - fz)], dim=-3)
+
+    kornia = types.ModuleType("kornia")
+    color = types.ModuleType("kornia.color")
+    color.rgb_to_lab = rgb_to_lab
+    kornia.color = color
+    saved = {k: sys.modules.get(k) for k in ("kornia", "kornia.color")}
+    sys.modules.update({"kornia": kornia, "kornia.color": color})
+    try:
+        spec = importlib.util.spec_from_file_location("_ct_reference_icid", os.path.join(REFERENCE_ROOT, "utils", "icid.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod.icid
