@@ -15,4 +15,16 @@ t8 = np.rint(np.stack([t, t]) * 255).astype(np.uint8); r8 = np.rint(np.stack([r,
 batch.idt_frames_u8(t8, r8); batch.linear_transfer_frames_u8("reinhard", t8, r8)
 t, r = synthetic_pair(97, 131, 7, np.float64)
 np.random.seed(3); it.automated_color_grading(t, r)
+# round-1 second session: fp32 Lab chain incl. the patched toes, chunked two-stream batches, metrics
+import torch
+from color_transfer_b200 import _cabi, device, metrics
+rng = np.random.default_rng(9)
+dark = (rng.integers(0, 14, (35, 3, 23, 31)) / 255.0).astype(np.float32)
+dark[::3, :, ::4, ::5] = rng.random(dark[::3, :, ::4, ::5].shape, dtype=np.float32)
+tb = torch.from_numpy(np.ascontiguousarray(dark.transpose(0, 2, 3, 1))).cuda()
+device.linear_transfer(_cabi.CT_REINHARD, tb, tb.flip(0)); device.linear_transfer(_cabi.CT_MKL_MK, tb, tb.flip(0))
+x = torch.rand(2, 3, 75, 101, device="cuda"); y = (x * 0.8 + 0.1).clamp(0, 1)
+metrics.icid(x, y); metrics.icid(x, y, downsampling=False, omit_maps67=True); metrics.psnr(x, y)
+big = torch.rand(1, 3, 530, 300, device="cuda"); metrics.icid(big, big.flip(3))
+torch.cuda.synchronize()
 print("sanitizer workload done")
