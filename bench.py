@@ -513,6 +513,32 @@ def linear_extras(torch, device, synth, _cabi, handle, dev, peak):
         out[name] = {"Mpix/s": B * H * W / 1e6 / (ms / 1e3), "ms_per_batch": ms, "pairs": B, "shape": [H, W, 3],
                      "algorithmic_GBps": gbps, "frac_of_hbm": gbps / peak,
                      "note": "batch working set 1.2-2.0 GB, larger than L2"}
+    # configs[2] as named: the whole batch of 1035 pairs of 960x540 float32 in one call, primary
+    # (smooth field) and stress (i.i.d. uniform) distributions
+    del tgt, ref, dst
+    B2 = 1035
+    full = {}
+    for dist_name, stress in (("smooth-field+noise", False), ("uniform-noise", True)):
+        tgt, ref = synth.frame_pairs_cuda(B2, H, W, 1000, dev, stress=stress)
+        for name, method, bpp in (("reinhard_f32", _cabi.CT_REINHARD, 48), ("mkl_f32_to_f64", _cabi.CT_MKL_MK, 60)):
+            if stress and method != _cabi.CT_REINHARD:
+                continue
+            dst = torch.empty((B2, H, W, 3), dtype=torch.float32 if method == _cabi.CT_REINHARD else torch.float64, device=dev)
+            device.linear_transfer(method, tgt, ref, out=dst, handle=handle)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(3):
+                device.linear_transfer(method, tgt, ref, out=dst, handle=handle)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            gbps = bpp * B2 * H * W / (ms / 1e3) / 1e9
+            full[f"{name}/{dist_name}"] = {"Mpix/s": B2 * H * W / 1e6 / (ms / 1e3), "ms_per_batch": ms,
+                                           "algorithmic_GBps": gbps, "frac_of_hbm": gbps / peak}
+            del dst
+        del tgt, ref
+    out["config2_1035_pairs_960x540"] = full
     # configs[0] / configs[1] shape: one 1080x860 float64 pair (L2-resident, launch-latency regime)
     import numpy as np
     from color_transfer_b200 import batch
