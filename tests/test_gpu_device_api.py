@@ -170,21 +170,21 @@ def test_uint8_frame_io(mods, as_float32):
     assert np.array_equal(again, batch.idt_frames_u8(t8, r8, rotations=rot, as_float32=as_float32))
 
 
-def test_large_reinhard_batch_runs_chunked_on_two_streams(mods):
-    """Batches of >= 32 pairs go through the two-stream chunked driver (ct_linear_transfer): the
+def test_large_batches_run_chunked_on_two_streams(mods):
+    """Batches of >= 32 Mpix go through the two-stream chunked driver (ct_linear_transfer): the
     result must match the same pairs transferred one call at a time and the oracle."""
     torch, _cabi, batch, device, sharded, synth, oracle = mods
-    B, H, W = 37, 40, 52                                   # odd count: the last chunk is shorter
-    t, r = _stack(B, H, W, np.float32, seed=300)
-    dt, dr = torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda()
+    B, H, W = 71, 540, 960                                  # 36.8 Mpix: chunks of 36 and 35 pairs
+    dt, dr = synth.frame_pairs_cuda(B, H, W, 4000, "cuda")
     for code, fn, tol in ((_cabi.CT_REINHARD, oracle.color_transfer_between_images, 1e-4),
                           (_cabi.CT_MKL_MK, oracle.monge_kantorovitch_color_transfer, 1e-9)):
-        whole = device.linear_transfer(code, dt, dr).cpu().numpy()
-        for b in (0, 9, 10, 18, 27, 36):
-            single = device.linear_transfer(code, dt[b:b + 1], dr[b:b + 1]).cpu().numpy()[0]
-            assert np.max(np.abs(whole[b].astype(np.float64) - single)) <= 1e-6
-            ref = fn(t[b].astype(np.float64), r[b].astype(np.float64))
-            assert np.max(np.abs(whole[b] - ref)) <= tol
+        whole = device.linear_transfer(code, dt, dr)
+        for b in (0, 35, 36, 70):
+            single = device.linear_transfer(code, dt[b:b + 1], dr[b:b + 1])[0]
+            assert float((whole[b].double() - single.double()).abs().max()) <= 1e-6
+        for b in (35, 70):
+            ref = fn(dt[b].cpu().numpy().astype(np.float64), dr[b].cpu().numpy().astype(np.float64))
+            assert np.max(np.abs(whole[b].cpu().numpy() - ref)) <= tol
     torch.cuda.synchronize()
 
 
