@@ -39,6 +39,26 @@ METRIC = "stereopair Mpix/s (IDT, 4K stereo video, frame-parallel)"
 IDT_BYTES_PER_PIXEL_F32 = 24 + (24 + 36) + 3 * (36 + 48)
 
 
+# The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's "NCCL version ..."
+# banner under torchrun), so file descriptor 1 is pointed at stderr for the whole process and the
+# result line is written to a private duplicate of the original stdout.
+_RESULT_OUT = None
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def _claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -229,7 +249,7 @@ def run_reference_arm(a):
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(a, frames):
@@ -243,6 +263,7 @@ def workload_config(a, frames):
 # ------------------------------------------------------------------------------------------ our arm
 def main():
     a = parse_args()
+    _claim_stdout()
     if a.impl == "reference":
         run_reference_arm(a)
         return
@@ -280,7 +301,7 @@ def main():
         return float(t.item())
 
     if a.linear_only:
-        print(json.dumps(linear_extras(torch, device, synth, _cabi, handle, dev, measured_peaks()[0])))
+        emit(linear_extras(torch, device, synth, _cabi, handle, dev, measured_peaks()[0]))
         return
     if a.workload == "rowshard":
         run_rowshard(a, torch, dist, device, synth, _cabi, handle, dev, world, rank, barrier, max_over_ranks)
@@ -318,8 +339,8 @@ def main():
     value = world * F * npix / 1e6 / (ms_step / 1e3)
     if a.kernels_only:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": "Mpix/s", "ms_per_step": ms_step,
-                              "gpu_launches": int(launches), "note": "kernels-only profiling run"}))
+            emit({"metric": METRIC, "value": value, "unit": "Mpix/s", "ms_per_step": ms_step,
+                  "gpu_launches": int(launches), "note": "kernels-only profiling run"})
         return
 
     # ---- per-kernel breakdown with CUDA events (stage API == the same kernels, unfused LUT off)
@@ -432,7 +453,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, F),
                 "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu, "host_api_matches_device_api": same, "extras": extras}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -485,10 +506,10 @@ def run_rowshard(a, torch, dist, device, synth, _cabi, handle, dev, world, rank,
         results[name] = {"ms_per_pair": ms, "Mpix/s": npix / 1e6 / (ms / 1e3),
                          "frac_of_hbm_aggregate": bpp * npix / (ms / 1e3) / 1e9 / (peak * world), "collectives_per_pair": 1}
     if rank == 0:
-        print(json.dumps({"metric": "stereopair Mpix/s (one %dx%d pair, row-sharded)" % (side, side), "unit": "Mpix/s",
-                          "n_gpus": world, "scaling": "strong", "value": results["idt"]["Mpix/s"], "data": "synthetic",
-                          "config": {"workload": "configs[4]: single %dx%d float32 stereopair row-sharded with NCCL all-reduces" % (side, side),
-                                     "rows_per_rank": rows, "bins": BINS, "n_iter": N_ITER}, "results": results}))
+        emit({"metric": "stereopair Mpix/s (one %dx%d pair, row-sharded)" % (side, side), "unit": "Mpix/s",
+              "n_gpus": world, "scaling": "strong", "value": results["idt"]["Mpix/s"], "data": "synthetic",
+              "config": {"workload": "configs[4]: single %dx%d float32 stereopair row-sharded with NCCL all-reduces" % (side, side),
+                         "rows_per_rank": rows, "bins": BINS, "n_iter": N_ITER}, "results": results})
 
 
 def linear_extras(torch, device, synth, _cabi, handle, dev, peak):
