@@ -441,11 +441,10 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        hh, ww = H // 2, W // 2
-        v, wall, _ = cpu_oracle_throughput(hh, ww, 1, 1)
+        v, wall, _ = cpu_oracle_throughput(H, W, 1, 2)      # two full frame pairs: ~12 s of CPU work
         cpu = {"value": v, "unit": "Mpix/s", "cores": 1, "kind": "port",
-               "sample": f"one {ww}x{hh} quarter-area frame pair of the workload, float32 in, bins={BINS}, n_iter={N_ITER}, "
-                         f"single process ({wall:.1f} s); numpy oracle port of methods/iterative.py"}
+               "sample": f"two {W}x{H} frame pairs of the workload (of the {F} per step), float32 in, bins={BINS}, "
+                         f"n_iter={N_ITER}, single process ({wall:.1f} s); numpy oracle port of methods/iterative.py"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": a.steps,
