@@ -153,3 +153,24 @@ def test_header_is_plain_c_and_library_links_without_python(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, f"abi_smoke exit code {res.returncode}: {res.stdout}{res.stderr}"
     assert "abi_smoke ok" in res.stdout
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) needs no GPU: it must
+    print exactly one JSON line on stdout carrying the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--height", "96", "--width", "128"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, p.stdout
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "Mpix/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["metric"].startswith("stereopair Mpix/s")
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["config"]["workload"].startswith("configs[3]")
