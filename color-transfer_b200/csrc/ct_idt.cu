@@ -88,12 +88,13 @@ __device__ __forceinline__ bool not_finite(double p) {
     return (__double2hiint(p) & 0x7ff00000) == 0x7ff00000;
 }
 
-// fold per-thread minima of (p0,p1,p2,-p0,-p1,-p2) into the pair's keys
+// fold per-thread (min p0, min p1, min p2, max p0, max p1, max p2) into the pair's keys, which hold
+// the minima of (p, -p)
 __device__ __forceinline__ void fold_range(double (&mn)[6], int64_t *keys, double (*red)[6]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        const double v = warp_min(mn[i]);
+        const double v = warp_min(i < 3 ? mn[i] : -mn[i]);
         if (lane == 0) red[warp][i] = v;
     }
     __syncthreads();
@@ -105,17 +106,17 @@ __device__ __forceinline__ void fold_range(double (&mn)[6], int64_t *keys, doubl
     }
 }
 
-// Running minima of (p, -p).  Plain compare-select: fmin()'s NaN handling costs twice as many
+// Running (min, max) of p: mn[0..2] minima, mn[3..5] MAXIMA (tracking -p instead would cost a DADD
+// per sample on the fp64 pipe).  Plain compare-select: fmin()'s NaN handling costs twice as many
 // instructions, and non-finite samples are caught once, by K4 on the inputs (CHECK).
 template <bool CHECK>
 __device__ __forceinline__ void track_range(const double *rot, const double (&x)[3], double (&mn)[6], bool &bad) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const double p = dot3(rot + 3 * j, x);
-        const double q = -p;
         if (CHECK) bad |= not_finite(p);
         mn[j] = p < mn[j] ? p : mn[j];
-        mn[3 + j] = q < mn[3 + j] ? q : mn[3 + j];
+        mn[3 + j] = p > mn[3 + j] ? p : mn[3 + j];
     }
 }
 
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, NROT == 1 ? 3 : 2) ranges_kernel(Ran
 #pragma unroll
     for (int k = 0; k < NROT; ++k)
 #pragma unroll
-        for (int i = 0; i < 6; ++i) mn[k][i] = INFINITY;
+        for (int i = 0; i < 6; ++i) mn[k][i] = i < 3 ? INFINITY : -INFINITY;
     bool bad = false;
     switch (a.kind * 2 + a.vec) {
 #define CT_CASE(ID, T, L, V) \
@@ -628,7 +629,7 @@ __global__ void __launch_bounds__(kThreads, CT_MINB) remap_kernel(RemapArgs a) {
 
     double mn[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) mn[i] = INFINITY;
+    for (int i = 0; i < 6; ++i) mn[i] = i < 3 ? INFINITY : -INFINITY;
     bool bad = false;
     remap_dispatch<SIO, VEC>(a, pair, sh, sm_tab, pipe, next, mn, bad);
     if (next) fold_range(mn, a.keys_next + pair * a.keys_stride, sh.red);
