@@ -19,16 +19,18 @@ constexpr int pipe_bytes(int stages) { return stages * kTileBytes + 2 * stages *
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+// All helpers take 32-bit shared-window addresses: converting a generic pointer costs ~5
+// instructions (S2UR CgaCtaId, LEA, ...) and the tile loop would redo it for every stage.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -37,34 +39,47 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        "}" ::"r"(bar), "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// 128-bit / 64-bit loads from a 32-bit shared-window address
+template <typename V>
+__device__ __forceinline__ V lds_vec(uint32_t addr);
+template <>
+__device__ __forceinline__ float4 lds_vec<float4>(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+template <>
+__device__ __forceinline__ double2 lds_vec<double2>(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
 
-// Shared-memory view of one CTA's pipeline (carved from dynamic shared memory, 16 B aligned).
+// Shared-memory view of one CTA's pipeline (carved from dynamic shared memory, 16 B aligned):
+// kStages tiles, then per barrier set kStages "full" and kStages "empty" mbarriers.
 template <int kStages>
 struct Pipe {
     static constexpr int kNumStages = kStages;
-    unsigned char *stage;  // kStages * kTileBytes
-    uint64_t *full;        // [kStages]
-    uint64_t *empty;       // [kStages]
+    uint32_t stage;  // shared-window address of kStages * kTileBytes
+    uint32_t full;   // [kStages] x 8 B
+    uint32_t empty;  // [kStages] x 8 B
     // `set` selects one of several barrier sets laid out after the stages, so that a kernel can run
     // several pipelines one after the other over the same stage buffers (each starts at phase 0)
     __device__ __forceinline__ explicit Pipe(void *base, int set = 0)
-        : stage(static_cast<unsigned char *>(base)),
-          full(reinterpret_cast<uint64_t *>(static_cast<unsigned char *>(base) + kStages * kTileBytes) + 2 * kStages * set),
-          empty(full + kStages) {}
+        : stage(smem_u32(base)), full(stage + kStages * kTileBytes + 16 * kStages * set), empty(full + 8 * kStages) {}
     // one thread; followed by __syncthreads() in the caller
     __device__ __forceinline__ void init() {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kWarps);
+            mbar_init(full + 8 * s, 1);
+            mbar_init(empty + 8 * s, kWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -82,45 +97,45 @@ __device__ __forceinline__ void pipe_for_each_group(P &pipe, const typename IO::
     constexpr int G = IO::G;
     constexpr int kTilePx = kThreads * G;
     const int mine = first_tile < ntiles ? (ntiles - first_tile + tile_stride - 1) / tile_stride : 0;
-    auto issue = [&](int i) {  // thread 0 only
-        const int s = i % kStages;
+    auto issue = [&](int i, int s) {  // thread 0 only; s == i % kStages
         const int64_t p0 = (int64_t)(first_tile + (int64_t)i * tile_stride) * kTilePx;
-        unsigned char *dst = pipe.stage + s * kTileBytes;
-        mbar_expect_tx(&pipe.full[s], kTileBytes);
+        const uint32_t dst = pipe.stage + s * kTileBytes, bar = pipe.full + 8 * s;
+        mbar_expect_tx(bar, kTileBytes);
         if (IO::kLayout == CT_HWC) {
-            bulk_g2s(dst, img + 3 * p0, kTileBytes, &pipe.full[s]);
+            bulk_g2s(dst, img + 3 * p0, kTileBytes, bar);
         } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) bulk_g2s(dst + c * (kTileBytes / 3), img + c * plane + p0, kTileBytes / 3, &pipe.full[s]);
+            for (int c = 0; c < 3; ++c) bulk_g2s(dst + c * (kTileBytes / 3), img + c * plane + p0, kTileBytes / 3, bar);
         }
     };
     if (threadIdx.x == 0)
-        for (int i = 0; i < kStages && i < mine; ++i) issue(i);
+        for (int i = 0; i < kStages && i < mine; ++i) issue(i, i);
+    // this thread's group inside a stage
+    const uint32_t my_off = IO::kLayout == CT_HWC ? 48u * threadIdx.x : 16u * threadIdx.x;
+    int s = 0;
+    uint32_t parity = 0;
     for (int i = 0; i < mine; ++i) {
-        const int s = i % kStages;
-        const uint32_t parity = (i / kStages) & 1;
-        mbar_wait(&pipe.full[s], parity);
+        const uint32_t full = pipe.full + 8 * s, empty = pipe.empty + 8 * s;
+        mbar_wait(full, parity);
         typename IO::Raw raw;
         {
             using V = typename IO::V;
-            const unsigned char *src = pipe.stage + s * kTileBytes;
-            if (IO::kLayout == CT_HWC) {
-                const V *v = reinterpret_cast<const V *>(src) + 3 * threadIdx.x;
+            const uint32_t src = pipe.stage + s * kTileBytes + my_off;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) *reinterpret_cast<V *>(&raw.e[k * G]) = v[k];
-            } else {
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    *reinterpret_cast<V *>(&raw.e[c * G]) = reinterpret_cast<const V *>(src + c * (kTileBytes / 3))[threadIdx.x];
-            }
+            for (int k = 0; k < 3; ++k)
+                *reinterpret_cast<V *>(&raw.e[k * G]) = lds_vec<V>(src + (IO::kLayout == CT_HWC ? 16 * k : k * (kTileBytes / 3)));
         }
         __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(&pipe.empty[s]);  // this warp has copied its groups out
+        if ((threadIdx.x & 31) == 0) mbar_arrive(empty);  // this warp has copied its groups out
         if (threadIdx.x == 0 && i + kStages < mine) {
-            mbar_wait(&pipe.empty[s], parity);  // all 8 warps are done with the stage
-            issue(i + kStages);
+            mbar_wait(empty, parity);  // all 8 warps are done with the stage
+            issue(i + kStages, s);
         }
         f(raw, (int64_t)(first_tile + (int64_t)i * tile_stride) * kTilePx + (int64_t)threadIdx.x * G);
+        if (++s == kStages) {
+            s = 0;
+            parity ^= 1u;
+        }
     }
     (void)sizeof(T);
 }
