@@ -402,12 +402,17 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Hi
         inv[j] = sh.grid[j].inv;
         stp[j] = sh.grid[j].step;
     }
+    // this lane's copy of each axis histogram as a 32-bit shared-window address: the slot of bin k
+    // is one shift-add away (the generic-pointer form cost four integer instructions per sample)
+    uint32_t hb[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) hb[j] = smem_u32(hist) + 4u * (uint32_t)(((j * bins) << copies_log2) + copy);
     auto one = [&](const double(&x)[3]) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             const double p = dot3(r + 3 * j, x);
             const int k = bin_exact(p, lo[j], inv[j], stp[j], bins);
-            atomicAdd(&(hist + ((j * bins) << copies_log2) + copy)[k << copies_log2], 1u);
+            atomicAdd(reinterpret_cast<unsigned int *>(__cvta_shared_to_generic(hb[j] + ((uint32_t)k << (copies_log2 + 2)))), 1u);
         }
     };
     int64_t p = (int64_t)first_block * kThreads + threadIdx.x, step = (int64_t)nblocks * kThreads;
