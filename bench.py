@@ -606,6 +606,7 @@ def dropin_pair0964():
              ("iterative_distribution_transfer", methods.iterative.iterative_distribution_transfer, oracle.iterative_distribution_transfer),
              ("automated_color_grading", methods.iterative.automated_color_grading, oracle.automated_color_grading))
     for name, ours, ref in cases:
+        time.sleep(0.5)     # let the BLAS worker threads of the previous case's oracle call stop spinning
         np.random.seed(42)
         ours(left, right)
         t0 = time.perf_counter()
