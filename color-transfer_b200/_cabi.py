@@ -86,6 +86,8 @@ SIGNATURES = {
     "ct_icid": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]),
     "ct_psnr": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.c_int64, ctypes.POINTER(ctypes.c_double)]),
+    "ct_ssim": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                               ctypes.POINTER(ctypes.c_double)]),
 }
 
 _lib = None

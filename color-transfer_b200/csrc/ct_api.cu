@@ -384,6 +384,15 @@ int ct_psnr(ct_handle h, const float *x, const float *y, int32_t count, int64_t 
     return metric_result(h, result);
 }
 
+int ct_ssim(ct_handle h, const float *x, const float *y, int32_t count, int32_t height, int32_t width,
+            int32_t downsample, double *result) {
+    CT_ENTER(h);
+    if (!result) return fail(h, CT_E_INVALID, "result is NULL");
+    CT_TRY(ensure_scratch(h, 1));
+    CT_TRY(launch_ssim(h, x, y, count, height, width, downsample, h->sums));
+    return metric_result(h, result);
+}
+
 }  // extern "C"
 
 // Host pipeline shared by the two *_host entry points: per pair H2D on copy_in, kernels on the
@@ -438,9 +447,13 @@ int run_host_pipeline(ct_context *h, const ct_batch *target, const ct_batch *ref
     Pipeline pl;
     if (pl.init() != 0) return fail(h, CT_E_CUDA, "event creation failed");
     unsigned char *base = static_cast<unsigned char *>(h->stage);
-    // A single pair in pageable memory (the drop-in numpy call): bounce-buffered parallel copies
+    // A single pair in pageable memory (the drop-in numpy call): optional bounce-buffered parallel
+    // copies (CT_STAGED_COPY=1).  Off by default: 3.3-4.5 ms instead of 4.2-4.6 ms per 0964-size call
+    // on idle host cores, but 6 ms when other threads of the process are busy (e.g. BLAS workers
+    // still spinning after a numpy call) - the driver's own pageable path does not depend on that.
+    static const bool staged = getenv("CT_STAGED_COPY") != nullptr && atoi(getenv("CT_STAGED_COPY")) != 0;
     const size_t big = 2u << 20;
-    if (B == 1 && image_bytes(target) >= big && is_pageable(target->data) && is_pageable(reference->data) &&
+    if (staged && B == 1 && image_bytes(target) >= big && is_pageable(target->data) && is_pageable(reference->data) &&
         is_pageable(out->data)) {
         unsigned char *dt = base, *dr = dt + tb, *dout = dr + rb;
         static const bool prof = getenv("CT_PROFILE_HOST") != nullptr;

@@ -126,6 +126,7 @@ int launch_to_f64_hwc(ct_context *h, const ct_batch *img, double *out);
 int launch_icid(ct_context *h, const float *img1, const float *img2, int B, int H, int W, int intent,
                 int omit_maps67, int downsampling, double *out_dev);
 int launch_psnr(ct_context *h, const float *x, const float *y, int B, int64_t n, double *out_dev);
+int launch_ssim(ct_context *h, const float *x, const float *y, int B, int H, int W, int downsample, double *out_dev);
 
 // ct_idt.cu
 int launch_keys_init(ct_context *h, int64_t *keys, int64_t n);

@@ -7,7 +7,10 @@
 // in parallel.  Pinned / registered caller memory and small images keep the plain cudaMemcpyAsync.
 // Measured on the GPU box (CT_PROFILE_HOST=1): H2D of 2 x 22 MB 2.6 -> 1.9 ms, D2H of 22 MB into a
 // fresh array 1.3 -> 1.6 ms incl. the kernels; the host memory system (~27 GB/s of memcpy across
-// four threads) is the limit, so the whole call only goes from 4.2-4.6 to 3.4-4.0 ms.
+// four threads) is the limit, so the whole call goes from 4.2-4.6 to 3.3-4.5 ms on idle cores -
+// and to 6 ms when other threads of the process keep the cores busy (BLAS workers spinning after a
+// numpy call).  Hence OPT-IN (CT_STAGED_COPY=1, see run_host_pipeline); the default is the driver's
+// pageable cudaMemcpyAsync.
 #pragma once
 
 #include <atomic>

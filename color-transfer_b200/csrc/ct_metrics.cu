@@ -3,6 +3,7 @@
 //   iCID  ref: utils/icid.py:28-152   (bilinear downscale, Lab, seven SSIM-like maps from 11x11
 //                                      Gaussian statistics, 1 - mean of their product)
 //   PSNR  ref: methods/__init__.py:35 (piq.psnr defaults)
+//   SSIM  ref: methods/__init__.py:36 (piq.ssim defaults; kernels K11-K12 further down)
 // Images are planar float32 [B,3,H,W] (the tensors the reference hands to these metrics).
 //
 //   K8  icid_premaps_kernel   downscale + Lab of both images -> 11 planes L1 L2 C1 C2 L1^2 L2^2
@@ -234,6 +235,101 @@ __global__ void psnr_finish_kernel(const double *partials, int nblk, int B, doub
     if (threadIdx.x == 0) out[0] = total / B;
 }
 
+// ---------------------------------------------------------------------------------------------
+// SSIM (piq.ssim defaults, ref: methods/__init__.py:36): average-pool downscale, then per channel
+// the 11x11 Gaussian (sigma 1.5) statistics by VALID convolution and the mean of the SSIM map.
+//   K11 avgpool_kernel     [B,3,H,W] -> [B,3,oh,ow], f x f blocks (only when f > 1)
+//   K12 ssim_maps_kernel   per 32x32 output tile and plane: x and y tiles in shared memory, the
+//                          five statistics (x, y, xx, yy, xy) through one separable pass each,
+//                          SSIM per pixel, one partial sum per block
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) avgpool_kernel(const float *in, float *out, int H, int W, int oh, int ow, int f) {
+    const int ox = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (ox >= ow || oy >= oh) return;
+    const float *p = in + (int64_t)blockIdx.z * H * W + (int64_t)oy * f * W + (int64_t)ox * f;
+    float s = 0.0f;
+    for (int r = 0; r < f; ++r)
+        for (int c = 0; c < f; ++c) s += p[(int64_t)r * W + c];
+    out[(int64_t)blockIdx.z * oh * ow + (int64_t)oy * ow + ox] = s / (float)(f * f);
+}
+
+struct SsimArgs {
+    const float *x, *y;    // [planes][h][w]
+    double *partials;      // [planes * gridDim.y * gridDim.x]
+    int h, w;              // plane size; outputs are (h - 10) x (w - 10)
+    float c1, c2;
+    float k[11];
+};
+
+__global__ void __launch_bounds__(256) ssim_maps_kernel(SsimArgs a) {
+    __shared__ float tx[kIn][kIn + 1], ty[kIn][kIn + 1];
+    __shared__ float mid[kIn][kTile + 1];
+    __shared__ double red[8];
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * kTile, y0 = blockIdx.y * kTile;
+    const int64_t plane = (int64_t)a.h * a.w;
+    const float *px = a.x + blockIdx.z * plane, *py = a.y + blockIdx.z * plane;
+    for (int i = threadIdx.x; i < kIn * kIn; i += 256) {
+        const int r = i / kIn, c = i % kIn;
+        const int yy = min(y0 + r, a.h - 1), xx = min(x0 + c, a.w - 1);   // beyond the image: unused outputs
+        tx[r][c] = px[(int64_t)yy * a.w + xx];
+        ty[r][c] = py[(int64_t)yy * a.w + xx];
+    }
+    __syncthreads();
+    float v[4][5];
+    for (int q = 0; q < 5; ++q) {
+        for (int i = threadIdx.x; i < kIn * kTile; i += 256) {
+            const int r = i / kTile, c = i % kTile;
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 11; ++j) {
+                const float xv = tx[r][c + j], yv = ty[r][c + j];
+                const float t = q == 0 ? xv : q == 1 ? yv : q == 2 ? xv * xv : q == 3 ? yv * yv : xv * yv;
+                s = fmaf(a.k[j], t, s);
+            }
+            mid[r][c] = s;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int r = ly + 8 * m;
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 11; ++j) s = fmaf(a.k[j], mid[r + j][lx], s);
+            v[m][q] = s;
+        }
+        __syncthreads();
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int y = y0 + ly + 8 * m, x = x0 + lx;
+        if (y >= a.h - 10 || x >= a.w - 10) continue;
+        const float mx = v[m][0], my = v[m][1];
+        const float sxx = v[m][2] - mx * mx, syy = v[m][3] - my * my, sxy = v[m][4] - mx * my;
+        const float cs = (2.0f * sxy + a.c2) / (sxx + syy + a.c2);
+        acc += (double)((2.0f * mx * my + a.c1) / (mx * mx + my * my + a.c1) * cs);
+    }
+    acc = warp_sum(acc);
+    if (lx == 0) red[ly] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i];
+        a.partials[((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// out[0] = sum(partials) / count (every channel and image has the same number of map pixels, so
+// the mean of per-channel means is the overall mean)
+__global__ void mean_finish_kernel(const double *partials, int64_t n, double count, double *out) {
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 32) s += partials[i];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) out[0] = s / count;
+}
+
 }  // namespace
 
 int launch_icid(ct_context *h, const float *img1, const float *img2, int B, int H, int W, int intent,
@@ -291,6 +387,50 @@ int launch_psnr(ct_context *h, const float *x, const float *y, int B, int64_t n,
     sqdiff_kernel<<<dim3((unsigned)nblk, B), 256, 0, h->stream>>>(x, y, n, partials);
     psnr_finish_kernel<<<1, 32, 0, h->stream>>>(partials, (int)nblk, B, (double)n, out_dev);
     h->launches += 2;
+    CT_CUDA(h, cudaGetLastError());
+    return CT_OK;
+}
+
+int launch_ssim(ct_context *h, const float *x, const float *y, int B, int H, int W, int downsample, double *out_dev) {
+    if (!x || !y || !out_dev) return fail(h, CT_E_INVALID, "ssim: NULL argument");
+    if (B < 1 || H < 1 || W < 1 || (int64_t)B * 3 > 65535) return fail(h, CT_E_INVALID, "ssim: bad shape");
+    int f = (int)nearbyint((double)(H < W ? H : W) / 256.0);   // Python round(): half to even
+    if (f < 1 || !downsample) f = 1;
+    const int oh = H / f, ow = W / f, planes = 3 * B;
+    if (oh < 11 || ow < 11) return fail(h, CT_E_UNSUPPORTED, "ssim: image smaller than the 11x11 window after downscaling");
+    const dim3 grid((ow - 10 + kTile - 1) / kTile, (oh - 10 + kTile - 1) / kTile, planes);
+    const int64_t nparts = (int64_t)grid.x * grid.y * grid.z;
+    const size_t pooled = f > 1 ? (((size_t)planes * oh * ow * sizeof(float) + 255) & ~(size_t)255) : 0;
+    CT_TRY(ensure_ws(h, 2 * pooled + (size_t)nparts * sizeof(double)));
+    unsigned char *ws = static_cast<unsigned char *>(h->ws);
+    const float *sx = x, *sy = y;
+    int launches = 2;
+    if (f > 1) {
+        float *qx = reinterpret_cast<float *>(ws), *qy = reinterpret_cast<float *>(ws + pooled);
+        const dim3 g((ow + 31) / 32, (oh + 7) / 8, planes);
+        avgpool_kernel<<<g, 256, 0, h->stream>>>(x, qx, H, W, oh, ow, f);
+        avgpool_kernel<<<g, 256, 0, h->stream>>>(y, qy, H, W, oh, ow, f);
+        sx = qx;
+        sy = qy;
+        launches += 2;
+    }
+    SsimArgs a{};
+    a.x = sx;
+    a.y = sy;
+    a.partials = reinterpret_cast<double *>(ws + 2 * pooled);
+    a.h = oh;
+    a.w = ow;
+    a.c1 = 0.01f * 0.01f;
+    a.c2 = 0.03f * 0.03f;
+    double k[11], ksum = 0.0;   // piq gaussian_filter(11, 1.5): separable, normalised
+    for (int i = 0; i < 11; ++i) {
+        k[i] = exp(-(double)((i - 5) * (i - 5)) / (2.0 * 1.5 * 1.5));
+        ksum += k[i];
+    }
+    for (int i = 0; i < 11; ++i) a.k[i] = (float)(k[i] / ksum);
+    ssim_maps_kernel<<<grid, 256, 0, h->stream>>>(a);
+    mean_finish_kernel<<<1, 32, 0, h->stream>>>(a.partials, nparts, (double)planes * (oh - 10) * (ow - 10), out_dev);
+    h->launches += launches;
     CT_CUDA(h, cudaGetLastError());
     return CT_OK;
 }

@@ -2,8 +2,8 @@
 a batch dict of CHW tensors in, a stacked CHW float32 tensor out.  It is a LightningModule when
 pytorch_lightning is importable (so LightningCLI can drive it as in the reference) and a plain
 torch.nn.Module otherwise.  ``test_step`` computes the two quality metrics that have a device
-implementation here (PSNR and iCID, SURVEY.md section 8f-3, ``color_transfer_b200.metrics``); the
-reference's SSIM / FSIM come from piq and are not provided.
+implementation here (PSNR, SSIM and iCID, SURVEY.md section 8f-3, ``color_transfer_b200.metrics``);
+the reference's FSIM (piq) is not provided.
 
 Fast path: when the batch tensors already live on a CUDA device and the
 resolved function is one of this package's transfers, the whole batch is handed to the kernels
@@ -44,14 +44,14 @@ class Runner(_Base):
 
     def test_step(self, batch, batch_idx, dataloader_idx=0):
         """ref: methods/__init__.py:29-40 - clamp the result and score it against batch["gt"].
-        PSNR and iCID are computed on the device; returns (and, under Lightning, logs) them."""
-        from ..metrics import icid, psnr
+        PSNR, SSIM and iCID are computed on the device; returns (and, under Lightning, logs) them."""
+        from ..metrics import icid, psnr, ssim
         result = self(batch).clamp(0, 1)
         gt = batch["gt"]
         if not gt.is_cuda:
             gt = gt.cuda()
         result = result.to(gt.device)
-        values = {"Test PSNR": psnr(result, gt), "Test iCID": icid(result, gt)}
+        values = {"Test PSNR": psnr(result, gt), "Test SSIM": ssim(result, gt), "Test iCID": icid(result, gt)}
         if hasattr(self, "log"):
             for name, value in values.items():
                 self.log(name, value, prog_bar=name == "Test PSNR")

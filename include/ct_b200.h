@@ -223,6 +223,11 @@ int ct_idt_transfer_host_u8(ct_handle h, const uint8_t *target, const uint8_t *r
 int ct_icid(ct_handle h, const float *img1, const float *img2, int32_t count, int32_t height, int32_t width,
             int32_t intent, int32_t omit_maps67, int32_t downsampling, double *result);
 int ct_psnr(ct_handle h, const float *x, const float *y, int32_t count, int64_t elems_per_image, double *result);
+/* ct_ssim replaces piq.ssim(x, y) with its defaults (ref: methods/__init__.py:36): 11x11 Gaussian of
+ * sigma 1.5, valid convolution, k1 = 0.01, k2 = 0.03, average-pool downscale by
+ * max(1, round(min(H,W)/256)) when `downsample` != 0; mean over channels and batch. */
+int ct_ssim(ct_handle h, const float *x, const float *y, int32_t count, int32_t height, int32_t width,
+            int32_t downsample, double *result);
 
 #ifdef __cplusplus
 }

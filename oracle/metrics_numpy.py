@@ -8,8 +8,10 @@ Pinning: ``icid`` is checked against the UNMODIFIED ref: utils/icid.py executed 
 container (oracle/load_reference.py: real torch + torchvision, kornia.color.rgb_to_lab stubbed by
 the restatement below because kornia is not installed) — tests/golden/metrics.npz holds those
 values; the reference computes in float32, this restatement in float64, so they agree to ~1e-6,
-not bit for bit.  PARITY UNPINNED for ``psnr``: piq is neither vendored, pinned nor installed; the
-formula below is piq.psnr's published definition (data_range=1, reduction='mean', no greyscale).
+not bit for bit.  PARITY UNPINNED for ``psnr`` and ``ssim``: piq is neither vendored, pinned nor
+installed; the formulas below are piq.psnr's / piq.ssim's published definitions with their defaults
+(data_range=1, reduction='mean', no greyscale; SSIM: 11x11 Gaussian of sigma 1.5, valid
+convolution, k1=0.01, k2=0.03, average-pool downscale by max(1, round(min(H,W)/256))).
 """
 
 import numpy as np
@@ -118,3 +120,32 @@ def psnr(x, y, data_range=1.0):
     a, b = np.asarray(x, dtype=np.float64) / data_range, np.asarray(y, dtype=np.float64) / data_range
     mse = ((a - b) ** 2).reshape(a.shape[0], -1).mean(axis=1)
     return float(np.mean(-10.0 * np.log10(mse + 1e-8)))
+
+
+def ssim(x, y, kernel_size=11, kernel_sigma=1.5, k1=0.01, k2=0.03, downsample=True):
+    """piq.ssim(x, y) with its defaults on [B, 3, H, W] in [0, 1] (Wang et al. 2004): per channel
+    Gaussian-weighted local means / variances / covariance by VALID convolution, the mean of the
+    SSIM map per channel, then the mean over channels and over the batch."""
+    a, b = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    f = max(1, round(min(a.shape[-2:]) / 256))
+    if f > 1 and downsample:                      # torch.nn.functional.avg_pool2d(kernel_size=f)
+        oh, ow = a.shape[-2] // f, a.shape[-1] // f
+        a = a[..., :oh * f, :ow * f].reshape(*a.shape[:-2], oh, f, ow, f).mean(axis=(-3, -1))
+        b = b[..., :oh * f, :ow * f].reshape(*b.shape[:-2], oh, f, ow, f).mean(axis=(-3, -1))
+    t = np.arange(kernel_size) - (kernel_size - 1) / 2.0
+    g = np.exp(-(t[:, None] ** 2 + t[None, :] ** 2) / (2.0 * kernel_sigma ** 2))
+    g /= g.sum()
+    k1d = g.sum(axis=0)                            # the kernel is separable: rows of g sum to it
+    k1d_col = g.sum(axis=1)
+    h, w = a.shape[-2] - kernel_size + 1, a.shape[-1] - kernel_size + 1
+
+    def blur(v):
+        tmp = sum(k1d[i] * v[..., :, i:i + w] for i in range(kernel_size))
+        return sum(k1d_col[i] * tmp[..., i:i + h, :] for i in range(kernel_size))
+
+    c1, c2 = k1 ** 2, k2 ** 2
+    mu_x, mu_y = blur(a), blur(b)
+    s_xx, s_yy, s_xy = blur(a * a) - mu_x ** 2, blur(b * b) - mu_y ** 2, blur(a * b) - mu_x * mu_y
+    cs = (2 * s_xy + c2) / (s_xx + s_yy + c2)
+    ss = (2 * mu_x * mu_y + c1) / (mu_x ** 2 + mu_y ** 2 + c1) * cs
+    return float(ss.mean(axis=(-1, -2)).mean(axis=1).mean())

@@ -63,6 +63,28 @@ def test_oracle_psnr_definition():
     assert M.psnr(x, x) == pytest.approx(80.0, rel=1e-12)        # -10 log10(1e-8)
 
 
+def test_oracle_ssim_definition():
+    """The restatement against a direct conv2d transcription of the SSIM definition (Wang et al.
+    2004 with piq's defaults) and its basic properties."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(5)
+    x = rng.random((2, 3, 300, 340))
+    y = np.clip(x + 0.08 * rng.standard_normal(x.shape), 0, 1)
+    tx, ty = F.avg_pool2d(torch.from_numpy(x), 1), F.avg_pool2d(torch.from_numpy(y), 1)   # min side 300 -> factor 1
+    c = torch.arange(11, dtype=torch.float64) - 5
+    g = (-(c[None] ** 2 + c[:, None] ** 2) / (2 * 1.5 ** 2)).exp()
+    k = (g / g.sum())[None, None].repeat(3, 1, 1, 1)
+    mx, my = F.conv2d(tx, k, groups=3), F.conv2d(ty, k, groups=3)
+    sxx, syy = F.conv2d(tx * tx, k, groups=3) - mx ** 2, F.conv2d(ty * ty, k, groups=3) - my ** 2
+    sxy = F.conv2d(tx * ty, k, groups=3) - mx * my
+    ss = (2 * mx * my + 1e-4) / (mx ** 2 + my ** 2 + 1e-4) * (2 * sxy + 9e-4) / (sxx + syy + 9e-4)
+    assert M.ssim(x, y) == pytest.approx(float(ss.mean((-1, -2)).mean(1).mean()), abs=1e-12)
+    assert M.ssim(x, x) == pytest.approx(1.0, abs=1e-12)
+    assert M.ssim(x, y) == pytest.approx(M.ssim(y, x), abs=1e-12)
+    assert M.ssim(x, 1.0 - x) < 0.2
+
+
 # ------------------------------------------------------------------------------------------ GPU
 @pytest.fixture(scope="module")
 def dev_metrics():
@@ -124,3 +146,21 @@ def test_device_psnr_and_runner_test_step(dev_metrics):
     out = runner(batch).clamp(0, 1).cpu().numpy()
     assert float(vals["Test PSNR"]) == pytest.approx(M.psnr(out, x), abs=1e-3)
     assert float(vals["Test iCID"]) == pytest.approx(M.icid(out, x), abs=DEV_TOL)
+    assert float(vals["Test SSIM"]) == pytest.approx(M.ssim(out, x), abs=DEV_TOL)
+
+
+@pytest.mark.gpu
+def test_device_ssim_matches_oracle(dev_metrics):
+    torch, metrics = dev_metrics
+    rng = np.random.default_rng(11)
+    for b, h, w in ((2, 64, 80), (1, 300, 420), (1, 540, 960), (1, 11, 45), (1, 700, 1029)):   # factors 1, 1, 2, 1, 3
+        x = rng.random((b, 3, h, w), dtype=np.float32)
+        y = np.clip(x + 0.1 * rng.standard_normal(x.shape).astype(np.float32), 0, 1)
+        got = metrics.ssim(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda())
+        assert got.is_cuda and got.dtype == torch.float32
+        assert float(got) == pytest.approx(M.ssim(x, y), abs=2e-5), (b, h, w)
+    assert float(metrics.ssim(torch.from_numpy(x).cuda(), torch.from_numpy(x).cuda())) == pytest.approx(1.0, abs=1e-6)
+    assert float(metrics.ssim(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), downsample=False)) == \
+        pytest.approx(M.ssim(x, y, downsample=False), abs=2e-5)
+    with pytest.raises(Exception):
+        metrics.ssim(torch.rand(1, 3, 8, 40, device="cuda"), torch.rand(1, 3, 8, 40, device="cuda"))
