@@ -24,7 +24,7 @@ dark[::3, :, ::4, ::5] = rng.random(dark[::3, :, ::4, ::5].shape, dtype=np.float
 tb = torch.from_numpy(np.ascontiguousarray(dark.transpose(0, 2, 3, 1))).cuda()
 device.linear_transfer(_cabi.CT_REINHARD, tb, tb.flip(0)); device.linear_transfer(_cabi.CT_MKL_MK, tb, tb.flip(0))
 x = torch.rand(2, 3, 75, 101, device="cuda"); y = (x * 0.8 + 0.1).clamp(0, 1)
-metrics.icid(x, y); metrics.icid(x, y, downsampling=False, omit_maps67=True); metrics.psnr(x, y)
-big = torch.rand(1, 3, 530, 300, device="cuda"); metrics.icid(big, big.flip(3))
+metrics.icid(x, y); metrics.icid(x, y, downsampling=False, omit_maps67=True); metrics.psnr(x, y); metrics.ssim(x, y)
+big = torch.rand(1, 3, 530, 300, device="cuda"); metrics.icid(big, big.flip(3)); metrics.ssim(big, big.flip(3))
 torch.cuda.synchronize()
 print("sanitizer workload done")
