@@ -46,6 +46,9 @@ struct MomentsArgs {
 #ifndef CT_LAB_CTAS_PER_SM   // resident CTAs per SM the Lab kernels are compiled for (register cap)
 #define CT_LAB_CTAS_PER_SM 4
 #endif
+#ifndef CT_APPLY_CTAS_PER_SM   // the plain remap: 3 measured best (2: -2 %, 4: -5 %, 5: -25 %, spills)
+#define CT_APPLY_CTAS_PER_SM 3
+#endif
 #ifndef CT_LAB_APPLY_CTAS_PER_SM   // the Lab remap alone: fits 48 registers without spills, 5 measured best (4: -3 %, 6: -2 %)
 #define CT_LAB_APPLY_CTAS_PER_SM 5
 #endif
@@ -252,7 +255,7 @@ template <typename A, typename B> struct same_t { static constexpr bool value = 
 template <typename A> struct same_t<A, A> { static constexpr bool value = true; };
 
 template <typename SIO, typename DIO, bool VEC, bool LAB>
-__global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_APPLY_CTAS_PER_SM : 3) apply_kernel(ApplyArgs a) {
+__global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_APPLY_CTAS_PER_SM : CT_APPLY_CTAS_PER_SM) apply_kernel(ApplyArgs a) {
     using TS = typename SIO::elem_t;
     using TD = typename DIO::elem_t;
     // float32 in and out (Reinhard keeps the input dtype, linear.py:25-40): the hybrid chain
@@ -408,7 +411,7 @@ int launch_apply(ct_context *h, int method, const ct_batch *target, const double
     if (out->layout != CT_HWC) return fail(h, CT_E_UNSUPPORTED, "linear output must be CT_HWC");
     const bool vec = vec_ok(target) && vec_ok(out);
     const int group = target->dtype == CT_F32 ? 4 : 2;
-    const int nblk = blocks_for(h, target->npix, group, target->count, method == CT_REINHARD ? CT_LAB_APPLY_CTAS_PER_SM : 3,
+    const int nblk = blocks_for(h, target->npix, group, target->count, method == CT_REINHARD ? CT_LAB_APPLY_CTAS_PER_SM : CT_APPLY_CTAS_PER_SM,
                                 target->count == 1 ? 1 : (method == CT_REINHARD ? CT_APPLY_LAB_MIN_WAVES : CT_APPLY_MIN_WAVES));
     const dim3 grid(nblk, target->count);
     ApplyArgs a{img_of(target), imgout_of(out), xform};
