@@ -208,3 +208,26 @@ def test_reinhard_float32_toes_and_nan(mods):
     for t, r in ((bad, dark_r), (dark_r, bad)):
         out = device.linear_transfer(_cabi.CT_REINHARD, torch.from_numpy(t).cuda(), torch.from_numpy(r).cuda()).cpu().numpy()
         assert np.isnan(out).all()
+
+
+def test_bench_prints_one_contract_line(mods):
+    """bench.py (our arm, N=1): exactly one JSON line on stdout with the keys the driver reads."""
+    import json
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--frames", "2",
+                        "--e2e-frames", "2", "--no-extras"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, p.stdout[-2000:]
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["unit"] == "Mpix/s" and d["n_gpus"] == 1 and d["steps"] == 3 and d["scaling"] == "weak"
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["config"]["workload"].startswith("configs[3]")
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] < d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] == 1 and c["value"] > 0 and "sample" in c
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
