@@ -17,7 +17,7 @@
 #define CT_RANGES_CHUNK 4   // rotations evaluated per pass over a static image (1, 2 or 4)
 #endif
 #ifndef CT_HIST_STAGES
-#define CT_HIST_STAGES 4
+#define CT_HIST_STAGES 3
 #endif
 #ifndef CT_REMAP_STAGES
 #define CT_REMAP_STAGES 5
