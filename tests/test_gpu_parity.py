@@ -303,3 +303,34 @@ def test_idt_degenerate_ranges(api):
         assert np.array_equal(np.isnan(out), np.isnan(want)), name
         ok = ~np.isnan(want)
         assert np.max(np.abs(out[ok] - want[ok]), initial=0.0) < 1e-6, name
+
+
+def test_pair0964_notebook_and_cli_variants(api, pair0964):
+    """the notebook's input (target = adjust_hue(0964_L, 0.5), the big colour
+    mismatch the demo corrects; uint8 sha256 prefix 5d502d2bf161e98f) as float64, and the CLI's
+    marshalling of the same pair (float32 HWC views of CHW memory) against the float64 oracle."""
+    import hashlib
+    import os
+    from PIL import Image
+    from conftest import GOLDEN
+    tvf = pytest.importorskip("torchvision.transforms.functional")
+    lin, it, oracle = api
+    _, right = pair0964
+    hue = np.asarray(tvf.adjust_hue(Image.open(os.path.join(GOLDEN, "0964_L.png")).convert("RGB"), 0.5))
+    assert hashlib.sha256(hue.tobytes()).hexdigest().startswith("5d502d2bf161e98f")
+    target = hue / 255.0                                                       # skimage.img_as_float
+    _close(lin.color_transfer_between_images(target, right), oracle.color_transfer_between_images(target, right))
+    out = lin.monge_kantorovitch_color_transfer(target, right)
+    assert _close(out, oracle.monge_kantorovitch_color_transfer(target, right))[0] < 1e-9
+    np.random.seed(42)
+    out = it.iterative_distribution_transfer(target, right)
+    np.random.seed(42)
+    assert _close(out, oracle.iterative_distribution_transfer(target, right))[0] < 1e-9
+    # 1c: float32, CHW memory viewed HWC (ref: methods/__init__.py:21-22)
+    t32 = np.ascontiguousarray(target.astype(np.float32).transpose(2, 0, 1)).transpose(1, 2, 0)
+    r32 = np.ascontiguousarray(right.astype(np.float32).transpose(2, 0, 1)).transpose(1, 2, 0)
+    t64, r64 = t32.astype(np.float64), r32.astype(np.float64)
+    out = lin.color_transfer_between_images(t32, r32)
+    assert out.dtype == np.float32
+    _close(out, oracle.color_transfer_between_images(t64, r64))
+    _close(lin.monge_kantorovitch_color_transfer(t32, r32), oracle.monge_kantorovitch_color_transfer(t64, r64))
