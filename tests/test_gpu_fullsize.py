@@ -22,11 +22,12 @@ def mods():
     return torch, _cabi, device, sharded, synth, oracle, methods.linear, methods.iterative
 
 
-@pytest.mark.parametrize("index", [0, 1, 517, 1034])
-def test_config3_pairs_linear(mods, index):
-    """configs[2]: pair i of the 1035 synthetic 960x540 float32 pairs (seed 1000+i), Reinhard and MKL."""
+@pytest.mark.parametrize("index,stress", [(0, False), (1, False), (517, False), (1034, False), (0, True)])
+def test_config3_pairs_linear(mods, index, stress):
+    """configs[2]: pair i of the 1035 synthetic 960x540 float32 pairs (seed 1000+i), Reinhard and MKL;
+    primary (smooth field) distribution and, for pair 0, the i.i.d. uniform stress distribution."""
     torch, _cabi, device, sharded, synth, oracle, lin, it = mods
-    t, r = synth.frame_pair(540, 960, 1000 + index, np.float32)
+    t, r = synth.frame_pair(540, 960, 1000 + index, np.float32, stress=stress)
     t64, r64 = t.astype(np.float64), r.astype(np.float64)
     out = lin.color_transfer_between_images(t, r)
     want = oracle.color_transfer_between_images(t64, r64)
@@ -37,12 +38,14 @@ def test_config3_pairs_linear(mods, index):
     assert np.max(np.abs(out - oracle.monge_kantorovitch_color_transfer(t64, r64))) <= 1e-9
 
 
-def test_config4_frame_idt_against_oracle(mods):
-    """configs[3]: frame 0 of the synthetic 4K stereo video (seed 2000), float32, full oracle run."""
+@pytest.mark.parametrize("frame", [0, 599])
+def test_config4_frame_idt_against_oracle(mods, frame):
+    """configs[3]: frames 0 and 599 of the synthetic 4K stereo video (seed 2000 + k), float32, full
+    oracle run; the rotations of frame k are draws 4k..4k+3 after np.random.seed(42) (frame order)."""
     torch, _cabi, device, sharded, synth, oracle, lin, it = mods
-    t, r = synth.frame_pair(2160, 3840, 2000, np.float32)
+    t, r = synth.frame_pair(2160, 3840, 2000 + frame, np.float32)
     np.random.seed(42)
-    rot = sharded.predraw_rotations(1, 4)[0]
+    rot = sharded.predraw_rotations(frame + 1, 4)[frame]
     want, traces = oracle.idt_instrumented(t, r, rotations=rot, keep_arrays=False)
     trace = {}
     out = it.iterative_distribution_transfer(t, r, rotations=rot, trace=trace)
