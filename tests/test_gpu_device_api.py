@@ -96,15 +96,34 @@ def test_row_sharded_drivers_world1(mods):
         assert np.max(np.abs(a - b)) < 1e-12
 
 
+def _run_dist_check(nproc, port, same_device):
+    env = dict(os.environ)
+    if same_device:
+        env["CT_DIST_SAME_DEVICE"] = "1"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_gpu_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-6000:]
+    assert "DIST_GPU_CHECK_OK" in res.stdout
+    return res.stdout
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_sharding_ranks_on_one_gpu_vs_oracle(mods, world):
+    """SURVEY 8e / 8d config-5 protocol on a ONE-GPU box: `world` ranks share cuda:0 and all-reduce over
+    gloo, so the row-sharded drivers, their kernels and the collective schedule run where the driver's
+    pytest runs.  Inside: a 2048x2048 float32 pair of the config-5 generator, rows sharded, bit-identical
+    (counts and output) to the single-GPU run and bit-exact counts / <=1e-9 output against the CPU oracle;
+    world = 3 gives ragged row blocks (683/683/682 rows)."""
+    _run_dist_check(world, 29520 + world, same_device=True)
+
+
 def test_two_gpu_row_sharding_and_frame_parallel(mods):
+    """The same body, one GPU per rank over NCCL (the product configuration)."""
     torch = mods[0]
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tests", "dist_gpu_check.py")]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
-    assert "DIST_GPU_CHECK_OK" in res.stdout
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2); the one-GPU gloo variant above covers the same checks")
+    _run_dist_check(2, 29517, same_device=False)
 
 
 def test_runner_contract_host_and_device_paths(mods):
