@@ -31,7 +31,7 @@ def lut_doubles(bins):
 class Batch(ctypes.Structure):
     _fields_ = [("data", ctypes.c_void_p), ("npix", ctypes.c_int64), ("image_stride", ctypes.c_int64),
                 ("plane_stride", ctypes.c_int64), ("count", ctypes.c_int32), ("dtype", ctypes.c_int32),
-                ("layout", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("layout", ctypes.c_int32), ("flags", ctypes.c_int32)]
 
 
 class IdtStage(ctypes.Structure):

@@ -16,7 +16,7 @@ int check_batch(ct_context *h, const ct_batch *b, const char *name) {
     if (!b->data) return fail(h, CT_E_INVALID, "%s.data is NULL", name);
     if (b->npix <= 0) return fail(h, CT_E_INVALID, "%s.npix must be positive (got %lld)", name, (long long)b->npix);
     if (b->count <= 0) return fail(h, CT_E_INVALID, "%s.count must be positive", name);
-    if (b->dtype != CT_F32 && b->dtype != CT_F64) return fail(h, CT_E_INVALID, "%s.dtype unknown", name);
+    if (b->dtype != CT_F32 && b->dtype != CT_F64 && b->dtype != CT_U8) return fail(h, CT_E_INVALID, "%s.dtype unknown", name);
     if (b->layout != CT_HWC && b->layout != CT_CHW) return fail(h, CT_E_INVALID, "%s.layout unknown", name);
     if (b->count > 65535) return fail(h, CT_E_UNSUPPORTED, "%s.count above 65535 pairs per call", name);
     if (b->npix >= ((int64_t)1 << 31)) return fail(h, CT_E_UNSUPPORTED, "%s.npix must be below 2^31 pixels per image", name);
@@ -88,6 +88,8 @@ int ensure_stage(ct_context *h, size_t bytes) {
     return CT_OK;
 }
 
+int ensure_seed(ct_context *h, size_t words) { return grow(h, &h->seed, &h->seed_words, words, false); }
+
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct Carver {
@@ -154,11 +156,11 @@ static int idt_run(ct_context *h, const ct_batch *target, const ct_batch *refere
     CT_CUDA(h, cudaMemsetAsync(L.counts, 0, sizeof(uint64_t) * (size_t)B * 6 * bins, h->stream));
     CT_CUDA(h, cudaMemsetAsync(st, 0, sizeof(int32_t) * (size_t)B, h->stream));
     const int64_t keys_stride = (int64_t)(n_iter + 1) * CT_IDT_KEYS, rot_stride = (int64_t)n_iter * 9;
-    CT_TRY(launch_keys_init(h, L.keys, (int64_t)B * keys_stride));
     // iteration 0 needs the target's range; the reference never changes, so its range under
-    // EVERY rotation is taken in the same single pass over it
-    CT_TRY(launch_ranges(h, target, rotations, rot_stride, 1, L.keys, keys_stride, st));
-    CT_TRY(launch_ranges(h, reference, rotations, rot_stride, n_iter, L.keys, keys_stride, st));
+    // EVERY rotation is taken in the same single pass over it.  One seed launch (which also sets the
+    // keys to +inf) and one screened pass over both images.
+    CT_TRY(launch_ranges_pair(h, target, reference, n_iter, rotations, rot_stride, L.keys, keys_stride, st, L.keys,
+                              (int64_t)B * keys_stride));
 
     ct_batch state{};
     state.data = L.state;
@@ -208,6 +210,8 @@ int ct_create(int device, ct_handle *out) {
     h->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return CT_E_CUDA; }
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (const char *e = getenv("CT_RANGES_BOUND")) h->ranges_bound = (float)atof(e);
+    if (getenv("CT_RANGES_STATS") && cudaMalloc(&h->ranges_stats, 16) == cudaSuccess) cudaMemset(h->ranges_stats, 0, 16);
     if (cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
         delete h;
@@ -221,6 +225,13 @@ void ct_destroy(ct_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    if (h->ranges_stats) {   // diagnostics: how many pixels the K4 screen sent to the exact path
+        unsigned long long st[2] = {0, 0};
+        cudaMemcpy(st, h->ranges_stats, 16, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[ct] ranges screen: %llu pixels exact, %llu flagged repeats skipped\n", st[0], st[1]);
+        cudaFree(h->ranges_stats);
+    }
+    cudaFree(h->seed);
     cudaFree(h->partials);
     cudaFree(h->tickets);
     cudaFree(h->xform);

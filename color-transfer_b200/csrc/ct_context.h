@@ -32,8 +32,14 @@ struct ct_context {
     void *stage = nullptr;
     size_t stage_bytes = 0;
 
+    // K4 screen: pixels with |x0|+|x1|+|x2| above this take the exact fp64 path (CT_RANGES_BOUND)
+    float ranges_bound = 16.0f;
+    long long *seed = nullptr;                    // K4a -> K4b: subsample extremes [pairs][2][kSeedCtas][24]
+    size_t seed_words = 0;
+    unsigned long long *ranges_stats = nullptr;   // device [2], allocated when CT_RANGES_STATS is set
+
     bool hist_smem_raised = false;
-    bool remap_smem_raised[8] = {false, false, false, false, false, false, false, false};
+    bool remap_smem_raised[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
 
     // host pipeline
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
@@ -76,7 +82,7 @@ inline int fail(ct_context *h, int code, const char *fmt, ...) {
     } while (0)
 
 inline int src_kind(const ct_batch *b) { return b->dtype * 2 + b->layout; }
-inline size_t elem_size(int dtype) { return dtype == CT_F32 ? 4 : 8; }
+inline size_t elem_size(int dtype) { return dtype == CT_F32 ? 4 : (dtype == CT_U8 ? 1 : 8); }
 
 inline int64_t plane_of(const ct_batch *b) { return b->plane_stride ? b->plane_stride : b->npix; }
 
@@ -103,6 +109,7 @@ int ensure_scratch(ct_context *h, int pairs);
 int ensure_partials(ct_context *h, size_t doubles);
 int ensure_ws(ct_context *h, size_t bytes);
 int ensure_stage(ct_context *h, size_t bytes);
+int ensure_seed(ct_context *h, size_t words);
 
 // ct_linear.cu
 int launch_moments(ct_context *h, const ct_batch *a, const ct_batch *b, int lab, double *sums,
@@ -132,6 +139,9 @@ int launch_ssim(ct_context *h, const float *x, const float *y, int B, int H, int
 int launch_keys_init(ct_context *h, int64_t *keys, int64_t n);
 int launch_ranges(ct_context *h, const ct_batch *img, const double *rot, int64_t rot_stride, int n_rot,
                   int64_t *keys, int64_t keys_stride, int32_t *status);
+int launch_ranges_pair(ct_context *h, const ct_batch *target, const ct_batch *reference, int n_rot_r,
+                       const double *rot, int64_t rot_stride, int64_t *keys, int64_t keys_stride, int32_t *status,
+                       int64_t *init_keys, int64_t n_init);
 int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt_trace *trace,
                 int trace_iter, int trace_niter);
 int launch_lut(ct_context *h, const ct_idt_stage *s, int keep_counts, const ct_idt_trace *trace,

@@ -24,8 +24,14 @@
 #endif
 namespace ct {
 
-constexpr int kRangesStages = 3, kHistStages = CT_HIST_STAGES, kRemapStages = CT_REMAP_STAGES;
-using RangesPipe = Pipe<kRangesStages>;
+#ifndef CT_RANGES_STAGES1
+#define CT_RANGES_STAGES1 3   // tile stages of the one-rotation pass (4 CTAs per SM)
+#endif
+#ifndef CT_RANGES_STAGES4
+#define CT_RANGES_STAGES4 4   // ... of the two- and four-rotation passes (3 CTAs per SM)
+#endif
+constexpr int ranges_stages(int nrot) { return nrot == 1 ? CT_RANGES_STAGES1 : CT_RANGES_STAGES4; }
+constexpr int kHistStages = CT_HIST_STAGES, kRemapStages = CT_REMAP_STAGES;
 using HistPipe = Pipe<kHistStages>;
 // hist kernel dynamic shared memory: stages + two barrier sets (one per image), then the histograms
 constexpr int kHistSmemFront = kHistStages * kTileBytes + 2 * (2 * kHistStages * 8);
@@ -129,93 +135,371 @@ __global__ void keys_init_kernel(int64_t *keys, int64_t n) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K4: projected range of one image under one rotation (iterative.py:34-35, 39-40)
+// K4: projected ranges of an image under up to kMaxRot rotations in one pass (iterative.py:34-35,
+// 39-40).
+//
+// The result must be the exact fp64 minimum / maximum of p = rot_k[j] . x (it defines the bin grid),
+// but evaluating 3 DFMA-chains and 6 fp64 compare-selects per pixel and rotation made the pass
+// instruction-bound (round 1: 36 instructions per pixel and rotation, 0.27 of the HBM roofline).
+// Almost no pixel can move an extreme, so the work is split:
+//   K4a `ranges_seed_kernel`: exact fp64 ranges of a 1/64 subsample spread over the whole image
+//        (runs of 8 pixels), one partial result per seed CTA - a few microseconds.
+//   K4b `ranges_kernel`: every pixel is SCREENED in packed fp32 (FFMA2: two directions per
+//        instruction).  With c, h the centre and half width of an interval safely inside the seed's
+//        exact extremes, the rotation rows are pre-scaled by 1/h, so a pixel whose fp32 values
+//        d = (r/h) . x - c/h all satisfy |d| < 1 cannot change any extreme and is done after 3 FFMA2
+//        per direction pair and one 3-input maximum of the absolute values.  Only flagged pixels
+//        (beyond the sample's range, or tying an extreme) take the exact fp64 path, which folds them
+//        into the CTA's exact extremes (monotone int64 keys in shared memory, seeded with the sample's).
+// The answer is exactly the fp64 minimum / maximum whatever the screen does: the seed's extremes are
+// projections of real pixels, and the screen can only send too many pixels to the exact path, never
+// too few (error bound below).
+//
+// Error bound of the screen.  d = fma(r2,x2, fma(r1,x1, fma(r0,x0,c'))) in fp32 with r = fl32(rot/h),
+// c' = fl32(-c/h) and x = fl32(pixel): |d - (p - c)/h| <= 2^-24 (2 S + |c| + 3 (S + |c|)) / h (1 + o(1))
+// with S = |x0|+|x1|+|x2| (|rot| <= 1).  With S <= bound this is below delta / h,
+// delta = 2^-21 (bound + |c|); pixels with S > bound (or NaN) are always flagged.  h is the half width
+// of [lo + delta, hi - delta] about c, so |d| < 1 implies lo <= p <= hi.
 // ---------------------------------------------------------------------------------------------
-constexpr int kMaxRot = 4;  // most rotations one pass can take
+#ifndef CT_SEED_FRACTION
+#define CT_SEED_FRACTION 128   // K4a samples one pixel in this many
+#endif
+constexpr int kMaxRot = 4;     // most rotations one pass can take
+constexpr int kSeedCtas = 32;  // seed CTAs (partial results) per image
+constexpr int kSeedRun = 8;    // consecutive pixels per sampled run
 
 struct RangesArgs {
-    Img img;
-    int kind, vec;
-    int n_rot;  // 1..kMaxRot consecutive rotations (rot + 9k) folded into consecutive key slots (keys + 6k)
+    Img img[2];      // up to two images per pair in one launch (target, then reference)
+    int kind[2], vec[2];
+    int n_rot[2];    // 0: image absent; else rotations rot + 9k -> key slots keys + 6k, k < n_rot
+    int u8_as_f32[2];  // uint8 images: decode k/255 in float32 (else float64)
     const double *rot;
     int64_t rot_stride;
     int64_t *keys;
     int64_t keys_stride;
     int32_t *status;
+    float bound;     // screen validity bound on |x0|+|x1|+|x2| (pixels beyond it take the exact path)
+    long long *seed; // [B][2][kSeedCtas][6 * kMaxRot] keys of the subsample's extremes (K4a -> K4b)
+    int64_t *init_keys;   // K4a also sets these n_init keys to "+inf" (what keys_init_kernel does)
+    int64_t n_init;
+    unsigned long long *stats;  // optional diagnostics: [0] pixels sent to the exact path, [1] flagged repeats skipped
+    int which;       // K4b: the image slot this launch streams
 };
 
-template <typename IO, bool VEC, int NROT>
-__device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, const double *rot, int n_rot, RangesPipe &pipe,
-                                             int first_block, int nblocks, double (&mn)[NROT][6], bool &bad) {
+__device__ __forceinline__ int64_t seed_samples(int64_t npix) {
+    const int64_t want = npix / CT_SEED_FRACTION > 4096 ? npix / CT_SEED_FRACTION : 4096;
+    return want < npix ? want : npix;
+}
+
+// K4a.  grid (kSeedCtas, B, 2): exact ranges of the subsample of image z of pair y; CTA 0 of the whole
+// grid also initialises the pair's range keys.
+__global__ void __launch_bounds__(kThreads, 2) ranges_seed_kernel(RangesArgs a) {
+    __shared__ double rot[9 * kMaxRot];
+    __shared__ double red[kWarps][6 * kMaxRot];
+    __shared__ double dec_d[256];
+    __shared__ float dec_f[256];
+    const int z = blockIdx.z;
+    const int64_t pair = blockIdx.y;
+    if (a.init_keys) {
+        const int64_t ncta = (int64_t)gridDim.x * gridDim.y * gridDim.z;
+        const int64_t cta = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        for (int64_t i = cta * kThreads + threadIdx.x; i < a.n_init; i += ncta * kThreads) a.init_keys[i] = kKeyPlusInf;
+    }
+    const int n_rot = a.n_rot[z];
+    if (!n_rot) return;
+    if (threadIdx.x < 9 * n_rot) rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
+    fill_decode(dec_d, dec_f, a.u8_as_f32[z]);
+    __syncthreads();
+    const Decode dec{dec_d, dec_f};
+    const Img &im = a.img[z];
+    const int64_t nsamp = seed_samples(im.npix), step = im.npix / nsamp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // one rotation at a time (12 running extrema in registers); the sample is re-read from L2
+    for (int k = 0; k < n_rot; ++k) {
+        double mn[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) mn[i] = i < 3 ? INFINITY : -INFINITY;
+        bool bad = false;
+        auto sample = [&](auto io) {
+            using IO = decltype(io);
+            using T = typename IO::elem_t;
+            const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
+            // runs of kSeedRun pixels, one per cell of kSeedRun * step pixels, at a hashed offset inside the
+            // cell (a fixed offset would alias with the row length and sample only a few image columns)
+            const int64_t cell = kSeedRun * step, slack = cell - kSeedRun + 1;
+            for (int64_t i0 = (int64_t)blockIdx.x * kThreads + threadIdx.x; i0 < nsamp; i0 += 4 * (int64_t)gridDim.x * kThreads) {
+                double x[4][3];
+                bool have[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {   // four independent loads in flight per thread
+                    const int64_t i = i0 + u * (int64_t)gridDim.x * kThreads;
+                    const int64_t run = i / kSeedRun;
+                    const int64_t jitter = step == 1 ? 0 : (int64_t)(((uint32_t)run * 2654435761u) >> 8) % slack;
+                    const int64_t p = run * cell + jitter + (i % kSeedRun);
+                    have[u] = i < nsamp && p < im.npix;
+                    if (have[u]) IO::load1(base, im.plane_stride, p, dec, x[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (have[u]) track_range<false>(rot + 9 * k, x[u], mn, bad);
+            }
+        };
+        switch (a.kind[z]) {
+            case 0: sample(PixelIO<float, CT_HWC>{}); break;
+            case 1: sample(PixelIO<float, CT_CHW>{}); break;
+            case 2: sample(PixelIO<double, CT_HWC>{}); break;
+            case 3: sample(PixelIO<double, CT_CHW>{}); break;
+            case 4: sample(PixelIO<uint8_t, CT_HWC>{}); break;
+            default: sample(PixelIO<uint8_t, CT_CHW>{}); break;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const double v = warp_min(i < 3 ? mn[i] : -mn[i]);   // min p, min -p
+            if (lane == 0) red[warp][6 * k + i] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6 * n_rot) {
+        double v = red[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) v = fmin(v, red[w][threadIdx.x]);
+        // a NaN / inf sample leaves +-inf here: the main pass then flags every pixel (and reports it)
+        a.seed[((pair * 2 + z) * kSeedCtas + blockIdx.x) * (6 * kMaxRot) + threadIdx.x] = (long long)key_of(v);
+    }
+}
+
+struct RangesShared {
+    double rot[9 * kMaxRot];
+    long long key[kMaxRot][6];        // exact extremes so far: keys of min p [3], min -p [3], seeded by K4a
+    float scr[3 * kMaxRot + 1][4];    // per direction d = 3k + j: rot row / h [3], -c / h   ((0,0,0,2) = "flag everything")
+    int bad;
+    unsigned int n_exact, n_repeat;
+};
+
+template <int NP>
+struct Screen {
+    float2 r0[NP], r1[NP], r2[NP];  // rotation rows / h of directions (2i, 2i+1), fp32
+    float2 c[NP];                   // -c / h of the two directions
+};
+
+// screen row of one direction from its exact extremes so far: (rot row / h, -c / h)
+__device__ __forceinline__ void screen_row(const double *rot3, double lo, double hi, float bound, float (&out)[4]) {
+    out[0] = out[1] = out[2] = 0.0f;
+    out[3] = 2.0f;   // |d| = 2: flag every pixel
+    if (!(lo < hi)) return;
+    const float c32 = (float)(0.5 * (lo + hi));
+    const double c = (double)c32;
+    const double delta = ((double)bound + fabs(c)) * 4.76837158203125e-07 + 7.888609052210118e-31;  // 2^-21, 2^-100
+    const double h = fmin((hi - delta) - c, c - (lo + delta));
+    if (!(h > 1e-30) || !(h < 1e18) || !(fabs(c) < 1e18)) return;
+    const double inv = 1.0 / h;
+    out[0] = (float)(rot3[0] * inv);
+    out[1] = (float)(rot3[1] * inv);
+    out[2] = (float)(rot3[2] * inv);
+    out[3] = (float)(-c * inv);
+    if (!(fabsf(out[0]) < 1e30f && fabsf(out[1]) < 1e30f && fabsf(out[2]) < 1e30f && fabsf(out[3]) < 1e30f)) {
+        out[0] = out[1] = out[2] = 0.0f;
+        out[3] = 2.0f;
+    }
+}
+
+// true: the pixel may move an extreme (or cannot be screened) and must take the exact path
+template <int NP>
+__device__ __forceinline__ bool screen_flag(const Screen<NP> &s, const float (&x)[3], float bound) {
+    const float2 x0 = make_float2(x[0], x[0]), x1 = make_float2(x[1], x[1]), x2 = make_float2(x[2], x[2]);
+    float m = 0.0f;   // max |d| over the directions (a NaN d is dropped here; only a non-finite pixel makes one)
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        float2 d = __ffma2_rn(s.r0[i], x0, s.c[i]);
+        d = __ffma2_rn(s.r1[i], x1, d);
+        d = __ffma2_rn(s.r2[i], x2, d);
+        m = fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), m);
+    }
+    const float sum = fabsf(x[0]) + fabsf(x[1]) + fabsf(x[2]);
+    return !(sum <= bound) || !(m < 1.0f);
+}
+
+// exact path of one pixel: fold p and -p of rotations [k0, k1) into the CTA's keys
+__device__ __noinline__ void ranges_exact_pixel(RangesShared &sh, double x0, double x1, double x2, int k0, int k1) {
+    const double x[3] = {x0, x1, x2};
+    for (int k = k0; k < k1; ++k) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double p = dot3(sh.rot + 9 * k + 3 * j, x);
+            if (not_finite(p)) sh.bad = 1;
+            const long long klo = (long long)key_of(p), khi = (long long)key_of(-p);
+            if (klo < *(volatile long long *)&sh.key[k][j]) atomicMin(&sh.key[k][j], klo);
+            if (khi < *(volatile long long *)&sh.key[k][3 + j]) atomicMin(&sh.key[k][3 + j], khi);
+        }
+    }
+}
+
+// A pixel that ties an extreme (saturated white, letterbox black) stays inside the screen's error
+// band for ever: each thread remembers the last two distinct pixels it folded exactly and skips
+// their repeats.
+struct KnownPixels {
+    double a[3] = {NAN, NAN, NAN}, b[3] = {NAN, NAN, NAN};
+    __device__ __forceinline__ bool seen(const double (&x)[3]) const {
+        return (x[0] == a[0] && x[1] == a[1] && x[2] == a[2]) || (x[0] == b[0] && x[1] == b[1] && x[2] == b[2]);
+    }
+    __device__ __forceinline__ void push(const double (&x)[3]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            b[c] = a[c];
+            a[c] = x[c];
+        }
+    }
+};
+
+// NROT = rotations one thread screens.  SPLIT = 2: the CTA's two halves (warps 0-3 / 4-7) take rotations
+// [0, NROT) / [NROT, 2 NROT) of the pass and every thread visits two groups per tile - half the screen
+// state per thread (24 instead of 48 registers), which is what lets three CTAs share an SM.
+template <typename IO, bool VEC, int NROT, int SPLIT, typename RangesPipe>
+__device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, RangesShared &sh, const Decode &dec, int n_rot,
+                                             float bound, RangesPipe &pipe, int first_block, int nblocks, bool stats) {
     using T = typename IO::elem_t;
+    constexpr int NP = (3 * NROT + 1) / 2;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
-    constexpr int G = IO::G;
-    auto group = [&](const double(*x)[3], int n) {
+    constexpr int G = IO::G, GS = IO::GS;
+    const int half = SPLIT == 1 ? 0 : threadIdx.x / (kThreads / SPLIT);
+    const int d0 = 3 * NROT * half;   // first direction of this thread
+    Screen<NP> s;   // fixed for the whole pass; unused directions (k >= n_rot) are all-zero rows: d = 0, always inside
 #pragma unroll
-        for (int k = 0; k < NROT; ++k) {
-            if (NROT == 1 || k < n_rot) {
-                double r[9];
+    for (int i = 0; i < NP; ++i) {
+        const int da = d0 + 2 * i, db = d0 + 2 * i + 1;  // directions d = 3k + j <-> rot[3d .. 3d+2]
+        const bool ha = 2 * i < 3 * NROT && da < 3 * n_rot, hb = 2 * i + 1 < 3 * NROT && db < 3 * n_rot;
+        s.r0[i] = make_float2(ha ? sh.scr[da][0] : 0.0f, hb ? sh.scr[db][0] : 0.0f);
+        s.r1[i] = make_float2(ha ? sh.scr[da][1] : 0.0f, hb ? sh.scr[db][1] : 0.0f);
+        s.r2[i] = make_float2(ha ? sh.scr[da][2] : 0.0f, hb ? sh.scr[db][2] : 0.0f);
+        s.c[i] = make_float2(ha ? sh.scr[da][3] : 0.0f, hb ? sh.scr[db][3] : 0.0f);
+    }
+    // rotations the exact path of this thread folds: [k0, k1)
+    const int k0 = NROT * half, k1 = min(n_rot, NROT * (half + 1));
+    unsigned int n_exact = 0, n_repeat = 0;
+    KnownPixels known;
+    auto exact = [&](const double (&x)[3]) {
+        if (known.seen(x)) {
+            ++n_repeat;
+            return;
+        }
+        ranges_exact_pixel(sh, x[0], x[1], x[2], k0, k1);
+        known.push(x);
+        ++n_exact;
+    };
+    auto group = [&](const typename IO::Raw &raw) {
 #pragma unroll
-                for (int i = 0; i < 9; ++i) r[i] = rot[9 * k + i];   // shared-memory broadcast
+        for (int q = 0; q < IO::NSUB; ++q) {
+            float xf[GS][3];
+            IO::unpack_sub_f(raw, q, dec, xf);
+            bool flag[GS], any = false;
 #pragma unroll
-                for (int i = 0; i < G; ++i)
-                    if (i < n) {
-                        if (k == 0) track_range<true>(r, x[i], mn[k], bad);
-                        else track_range<false>(r, x[i], mn[k], bad);
-                    }
+            for (int i = 0; i < GS; ++i) {
+                flag[i] = screen_flag<NP>(s, xf[i], bound);
+                any |= flag[i];
+            }
+            if (any) {
+                double x[GS][3];
+                IO::unpack_sub(raw, q, dec, x);
+#pragma unroll
+                for (int i = 0; i < GS; ++i)
+                    if (flag[i]) exact(x[i]);
             }
         }
     };
     int64_t p = (int64_t)first_block * kThreads + threadIdx.x, step = (int64_t)nblocks * kThreads;
     if (VEC) {
         const int ntiles = (int)(im.npix / (kThreads * G));
-        pipe_for_each_group<IO>(pipe, base, im.plane_stride, ntiles, first_block, nblocks,
-                                [&](const typename IO::Raw &raw, int64_t) {
-                                    double x[G][3];
-                                    IO::unpack(raw, x);
-                                    group(x, G);
-                                });
+        if constexpr (SPLIT == 1)
+            pipe_for_each_group<IO>(pipe, base, im.plane_stride, ntiles, first_block, nblocks,
+                                    [&](const typename IO::Raw &raw, int64_t) { group(raw); });
+        else
+            pipe_for_each_group<IO, SPLIT>(pipe, base, im.plane_stride, ntiles, first_block, nblocks,
+                                           [&](const typename IO::Raw &raw, int64_t, int) { group(raw); });
         p = (int64_t)ntiles * kThreads * G + threadIdx.x;   // the tail belongs to block 0
         step = kThreads;
-        if (first_block != 0) return;
+        if (first_block != 0) p = im.npix;
+    }
+    // scalar pixels (tails, unaligned images): each half of a split CTA must see every one of them,
+    // so a half acts as a block of kThreads / SPLIT threads
+    if (SPLIT > 1) {
+        const int vt = threadIdx.x % (kThreads / SPLIT);
+        if (VEC) {
+            p = p - threadIdx.x + vt;
+            step = kThreads / SPLIT;
+        } else {
+            p = (int64_t)first_block * (kThreads / SPLIT) + vt;
+            step = (int64_t)nblocks * (kThreads / SPLIT);
+        }
     }
     for (; p < im.npix; p += step) {
-        double x[G][3];
-        IO::load1(base, im.plane_stride, p, x[0]);
-        group(x, 1);
+        double x[3];
+        IO::load1(base, im.plane_stride, p, dec, x);
+        const float xf[3] = {(float)x[0], (float)x[1], (float)x[2]};
+        if (screen_flag<NP>(s, xf, bound)) exact(x);
+    }
+    if (stats) {   // diagnostics only (CT_RANGES_STATS)
+        atomicAdd(&sh.n_exact, n_exact);
+        atomicAdd(&sh.n_repeat, n_repeat);
     }
 }
 
-template <int NROT>  // rotations per pass: registers hold NROT x 6 running minima
-__global__ void __launch_bounds__(kThreads, NROT == 1 ? 3 : 2) ranges_kernel(RangesArgs a) {
+#ifndef CT_RANGES_MINB
+#define CT_RANGES_MINB 3    // resident CTAs per SM the two- / four-rotation pass is compiled for
+#endif
+#ifndef CT_RANGES_MINB1
+#define CT_RANGES_MINB1 4   // ... the one-rotation pass
+#endif
+// One image (slot a.which) per launch, one instantiation per (source kind, vectorised, rotations per
+// pass) so that every variant gets its own register allocation: NROT = 1 (the target's iteration-0
+// range), 2, or 4 (split over the CTA's halves).
+template <typename IO, bool VEC, int NROT>
+__global__ void __launch_bounds__(kThreads, NROT == 1 ? CT_RANGES_MINB1 : CT_RANGES_MINB) ranges_kernel(RangesArgs a) {
     extern __shared__ __align__(16) unsigned char sm_pipe[];
+    __shared__ RangesShared sh;
+    __shared__ double dec_d[IO::kU8 ? 256 : 1];
+    __shared__ float dec_f[IO::kU8 ? 256 : 1];
+    const Decode dec{dec_d, dec_f};
     const int64_t pair = blockIdx.y;
-    __shared__ double rot[9 * kMaxRot];
-    __shared__ double red[kWarps][6];
-    RangesPipe pipe(sm_pipe);
-    if (threadIdx.x == 0) pipe.init();
-    if (threadIdx.x < 9 * a.n_rot) rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
-    __syncthreads();
-    double mn[NROT][6];
-#pragma unroll
-    for (int k = 0; k < NROT; ++k)
-#pragma unroll
-        for (int i = 0; i < 6; ++i) mn[k][i] = i < 3 ? INFINITY : -INFINITY;
-    bool bad = false;
-    switch (a.kind * 2 + a.vec) {
-#define CT_CASE(ID, T, L, V) \
-    case ID: ranges_image<PixelIO<T, L>, V, NROT>(a.img, pair, rot, a.n_rot, pipe, blockIdx.x, gridDim.x, mn, bad); break;
-        CT_FOR_EACH_SRC(CT_CASE)
-#undef CT_CASE
+    const int z = a.which;
+    const int n_rot = a.n_rot[z];
+    Pipe<ranges_stages(NROT)> pipe(sm_pipe);
+    if (threadIdx.x == 0) {
+        pipe.init();
+        sh.bad = 0;
+        sh.n_exact = sh.n_repeat = 0;
     }
-#pragma unroll
-    for (int k = 0; k < NROT; ++k) {
-        if (k < a.n_rot) {
-            fold_range(mn[k], a.keys + pair * a.keys_stride + CT_IDT_KEYS * k, red);
-            __syncthreads();
+    if (IO::kU8) fill_decode(dec_d, dec_f, a.u8_as_f32[z]);
+    if (threadIdx.x < 9 * n_rot) sh.rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
+    if (threadIdx.x < 6 * kMaxRot) (&sh.key[0][0])[threadIdx.x] = (long long)kKeyPlusInf;
+    __syncthreads();
+    {   // the subsample's extremes: kSeedCtas partial results per key
+        const long long *sd = a.seed + (pair * 2 + z) * kSeedCtas * (6 * kMaxRot);
+        for (int i = threadIdx.x; i < kSeedCtas * 6 * kMaxRot; i += kThreads) {
+            const int t = i % (6 * kMaxRot);
+            if (t < 6 * n_rot) {
+                const long long w = __ldcg(sd + i);
+                if (w < (long long)kKeyPlusInf) atomicMin(&(&sh.key[0][0])[t], w);
+            }
         }
     }
-    if (a.status && __syncthreads_or(bad) && threadIdx.x == 0) a.status[pair] = CT_E_NONFINITE;
+    __syncthreads();
+    if (threadIdx.x < 3 * n_rot) {
+        const int d = threadIdx.x, k = d / 3, j = d - 3 * k;
+        screen_row(sh.rot + 3 * d, value_of(sh.key[k][j]), -value_of(sh.key[k][3 + j]), a.bound, sh.scr[d]);
+    }
+    __syncthreads();
+    ranges_image<IO, VEC, (NROT > 2 ? NROT / 2 : NROT), (NROT > 2 ? 2 : 1)>(a.img[z], pair, sh, dec, n_rot, a.bound, pipe, blockIdx.x,
+                                                                            gridDim.x, a.stats != nullptr);
+    __syncthreads();
+    if (threadIdx.x < 6 * n_rot) {
+        const long long v = (&sh.key[0][0])[threadIdx.x];
+        if (v < (long long)kKeyPlusInf) atomicMin(reinterpret_cast<long long *>(a.keys + pair * a.keys_stride) + threadIdx.x, v);
+    }
+    if (a.status && threadIdx.x == 0 && sh.bad) a.status[pair] = CT_E_NONFINITE;
+    if (a.stats && threadIdx.x == 0) {
+        atomicAdd(a.stats + 0, (unsigned long long)sh.n_exact);
+        atomicAdd(a.stats + 1, (unsigned long long)sh.n_repeat);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -364,6 +648,7 @@ __global__ void __launch_bounds__(kThreads) lut_kernel(LutArgs a) {
 struct HistArgs {
     Img img[2];
     int kind[2], vec[2];
+    int u8_as_f32[2];
     int nblk[2];        // blocks of the target, blocks of the reference (either may be 0)
     const double *rot, *rot_next;
     int64_t rot_stride;
@@ -378,20 +663,24 @@ struct HistArgs {
     LutArgs lut;
 };
 
+template <bool U8>
 struct HistShared {
     double rot[9];
     AxisGrid grid[3];
     bool is_last;
+    double dec_d[U8 ? 256 : 1];
+    float dec_f[U8 ? 256 : 1];
 };
 
-template <typename IO, bool VEC, int CL2>  // CL2: log2(copies) when known at compile time, else -1
-__device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const HistShared &sh,
+template <typename IO, bool VEC, int CL2, typename Shared>  // CL2: log2(copies) when known at compile time, else -1
+__device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Shared &sh,
                                            int bins, int copies_log2_rt, unsigned int *hist, HistPipe &pipe,
                                            int first_block, int nblocks) {
     const int copies_log2 = CL2 >= 0 ? CL2 : copies_log2_rt;
     using T = typename IO::elem_t;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
-    constexpr int G = IO::G;
+    constexpr int G = IO::G, GS = IO::GS;
+    const Decode dec{sh.dec_d, sh.dec_f};
     const int copy = threadIdx.x & ((1 << copies_log2) - 1);
     double r[9], lo[3], inv[3], stp[3];
 #pragma unroll
@@ -420,10 +709,13 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Hi
         const int ntiles = (int)(im.npix / (kThreads * G));
         pipe_for_each_group<IO>(pipe, base, im.plane_stride, ntiles, first_block, nblocks,
                                 [&](const typename IO::Raw &raw, int64_t) {
-                                    double x[G][3];
-                                    IO::unpack(raw, x);
 #pragma unroll
-                                    for (int i = 0; i < G; ++i) one(x[i]);
+                                    for (int q = 0; q < IO::NSUB; ++q) {
+                                        double x[GS][3];
+                                        IO::unpack_sub(raw, q, dec, x);
+#pragma unroll
+                                        for (int i = 0; i < GS; ++i) one(x[i]);
+                                    }
                                 });
         p = (int64_t)ntiles * kThreads * G + threadIdx.x;   // the tail belongs to block 0
         step = kThreads;
@@ -431,16 +723,19 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Hi
     }
     for (; p < im.npix; p += step) {
         double x[3];
-        IO::load1(base, im.plane_stride, p, x);
+        IO::load1(base, im.plane_stride, p, dec, x);
         one(x);
     }
 }
 
+// ANY_U8: the instantiation that also holds the uint8 variants (launched when either image is uint8);
+// float / double images run the instantiation without them.
+template <bool ANY_U8>
 __global__ void __launch_bounds__(kThreads, 3) hist_kernel(HistArgs a) {
     // tile pipeline (stages, then one barrier set per image) | histograms; the front is later
     // reused by the LUT build
     extern __shared__ __align__(16) double sm_dyn[];
-    __shared__ HistShared sh;
+    __shared__ HistShared<ANY_U8> sh;
     const int64_t pair = blockIdx.y;
     const int bins = a.bins;
     unsigned int *hist = reinterpret_cast<unsigned int *>(sm_dyn + kHistSmemFront / 8);
@@ -459,6 +754,7 @@ __global__ void __launch_bounds__(kThreads, 3) hist_kernel(HistArgs a) {
         if (!a.nblk[z]) continue;  // this image is absent (stage API)
         HistPipe pipe(sm_dyn, z);
         if (threadIdx.x == 0) pipe.init();
+        if (ANY_U8 && a.kind[z] >= 4) fill_decode(sh.dec_d, sh.dec_f, a.u8_as_f32[z]);
         for (int i = threadIdx.x; i < nslots; i += kThreads) hist[i] = 0u;
         __syncthreads();
         const int sel = a.kind[z] * 2 + a.vec[z];
@@ -467,9 +763,21 @@ __global__ void __launch_bounds__(kThreads, 3) hist_kernel(HistArgs a) {
 #define CT_CASE_3(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, 3); break;
 #define CT_CASE_g(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, -1); break;
         if (a.copies_log2 == 3) {  // bins <= 256: the default 255
-            switch (sel) { CT_FOR_EACH_SRC(CT_CASE_3) }
+            switch (sel) {
+                CT_FOR_EACH_FLOAT_SRC(CT_CASE_3)
+                default:
+                    if constexpr (ANY_U8) {
+                        switch (sel) { CT_FOR_EACH_U8_SRC(CT_CASE_3) }
+                    }
+            }
         } else {
-            switch (sel) { CT_FOR_EACH_SRC(CT_CASE_g) }
+            switch (sel) {
+                CT_FOR_EACH_FLOAT_SRC(CT_CASE_g)
+                default:
+                    if constexpr (ANY_U8) {
+                        switch (sel) { CT_FOR_EACH_U8_SRC(CT_CASE_g) }
+                    }
+            }
         }
 #undef CT_HIST_CALL
 #undef CT_CASE_3
@@ -505,7 +813,10 @@ struct RemapArgs {
     Img src;
     ImgOut dst;
     int kind, vec;
-    int dst_layout;  // CT_CHW (planar fp64 state) or CT_HWC (final fp64 output)
+    int u8_as_f32;   // uint8 source: decode k/255 in float32 (else float64)
+    int dst_kind;    // kDstState (planar fp64 state), kDstF64 (final fp64 HWC), or a fused final conversion:
+                     // kDstU8 / kDstU8Planar (clip + round to uint8), kDstF32 (float32 HWC, optional clamp)
+    int clamp;
     const double *rot, *rot_next;
     int64_t rot_stride;
     int64_t *keys_next;
@@ -515,20 +826,27 @@ struct RemapArgs {
     int bins;
     int round_f32;
 };
+enum { kDstState = 0, kDstF64 = 1, kDstU8 = 2, kDstF32 = 3, kDstU8Planar = 4 };
 
+template <bool U8>
 struct RemapShared {
     double rot[18];
     AxisGrid grid[3];
     double red[kWarps][6];
+    double dec_d[U8 ? 256 : 1];
+    float dec_f[U8 ? 256 : 1];
 };
 
 template <typename SIO, typename DIO, bool VEC, bool NEXT, bool ROUND32>
-__device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, const RemapShared &sh,
+__device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, const RemapShared<SIO::kU8> &sh,
                                             const double *tab, RemapPipe &pipe, double (&mn)[6], bool &bad) {
     using TS = typename SIO::elem_t;
+    using TD = typename DIO::elem_t;
     const TS *src = reinterpret_cast<const TS *>(a.src.data) + pair * a.src.image_stride;
-    double *dst = reinterpret_cast<double *>(a.dst.data) + pair * a.dst.image_stride;
-    constexpr int G = SIO::G;
+    TD *dst = reinterpret_cast<TD *>(a.dst.data) + pair * a.dst.image_stride;
+    constexpr int G = SIO::G, GS = SIO::GS;
+    const Decode dec{sh.dec_d, sh.dec_f};
+    const bool clamp = a.clamp != 0;
     const int bins = a.bins;
     const int E = CT_IDT_EDGE_STRIDE(bins);
     double r[9], rn[9], lo[3], inv[3];
@@ -569,12 +887,15 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
     if (VEC) {
         const int ntiles = (int)(a.src.npix / (kThreads * G));
         pipe_for_each_group<SIO>(pipe, src, a.src.plane_stride, ntiles, blockIdx.x, gridDim.x,
-                                 [&](const typename SIO::Raw &raw, int64_t pix0) {
-                                     double x[G][3], y[G][3];
-                                     SIO::unpack(raw, x);
+                                 [&](const typename SIO::Raw &raw, int64_t tile0) {
 #pragma unroll
-                                     for (int i = 0; i < G; ++i) one(x[i], y[i]);
-                                     DIO::template store<true, G>(dst, a.dst.plane_stride, pix0, y);
+                                     for (int q = 0; q < SIO::NSUB; ++q) {
+                                         double x[GS][3], y[GS][3];
+                                         SIO::unpack_sub(raw, q, dec, x);
+#pragma unroll
+                                         for (int i = 0; i < GS; ++i) one(x[i], y[i]);
+                                         DIO::template store<true, GS>(dst, a.dst.plane_stride, pipe_sub_pixel0<SIO>(tile0, q), y, clamp);
+                                     }
                                  });
         p = (int64_t)ntiles * kThreads * G + threadIdx.x;   // the tail belongs to block 0
         step = kThreads;
@@ -582,28 +903,36 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
     }
     for (; p < a.src.npix; p += step) {
         double x[3], y[3];
-        SIO::load1(src, a.src.plane_stride, p, x);
+        SIO::load1(src, a.src.plane_stride, p, dec, x);
         one(x, y);
-        DIO::store1(dst, a.dst.plane_stride, p, y);
+        DIO::store1(dst, a.dst.plane_stride, p, y, clamp);
     }
 }
 
-// one instantiation per (source kind, vectorised); destination layout, NEXT and ROUND32 are
-// block-uniform runtime switches inside
+// one instantiation per (source kind, vectorised); destination, NEXT and ROUND32 are block-uniform
+// runtime switches inside.  The fused final conversions exist for the planar fp64 state as the
+// source only (the last of n_iter >= 2 iterations).
 template <typename SIO, bool VEC>
-__device__ __forceinline__ void remap_dispatch(const RemapArgs &a, int64_t pair, const RemapShared &sh,
+__device__ __forceinline__ void remap_dispatch(const RemapArgs &a, int64_t pair, const RemapShared<SIO::kU8> &sh,
                                                const double *tab, RemapPipe &pipe, bool next, double (&mn)[6], bool &bad) {
     using StateIO = PixelIO<double, CT_CHW>;
     using FinalIO = PixelIO<double, CT_HWC>;
+    constexpr bool kFromState = same_io<SIO, StateIO>::value && VEC;
+    if (kFromState && a.dst_kind >= kDstU8) {
+        if (a.dst_kind == kDstU8) remap_image<SIO, PixelIO<uint8_t, CT_HWC>, VEC, false, false>(a, pair, sh, tab, pipe, mn, bad);
+        else if (a.dst_kind == kDstU8Planar) remap_image<SIO, PixelIO<uint8_t, CT_CHW>, VEC, false, false>(a, pair, sh, tab, pipe, mn, bad);
+        else remap_image<SIO, PixelIO<float, CT_HWC>, VEC, false, false>(a, pair, sh, tab, pipe, mn, bad);
+        return;
+    }
     if (a.round_f32) {  // iteration 0 of float32 input: the state buffer is always the destination or n_iter == 1
-        if (a.dst_layout == CT_CHW) {
+        if (a.dst_kind == kDstState) {
             if (next) remap_image<SIO, StateIO, VEC, true, true>(a, pair, sh, tab, pipe, mn, bad);
             else remap_image<SIO, StateIO, VEC, false, true>(a, pair, sh, tab, pipe, mn, bad);
         } else {
             if (next) remap_image<SIO, FinalIO, VEC, true, true>(a, pair, sh, tab, pipe, mn, bad);
             else remap_image<SIO, FinalIO, VEC, false, true>(a, pair, sh, tab, pipe, mn, bad);
         }
-    } else if (a.dst_layout == CT_CHW) {
+    } else if (a.dst_kind == kDstState) {
         if (next) remap_image<SIO, StateIO, VEC, true, false>(a, pair, sh, tab, pipe, mn, bad);
         else remap_image<SIO, StateIO, VEC, false, false>(a, pair, sh, tab, pipe, mn, bad);
     } else {
@@ -615,7 +944,7 @@ __device__ __forceinline__ void remap_dispatch(const RemapArgs &a, int64_t pair,
 template <typename SIO, bool VEC>
 __global__ void __launch_bounds__(kThreads, CT_MINB) remap_kernel(RemapArgs a) {
     extern __shared__ __align__(16) double sm_remap[];  // tile pipeline | edges + {fp, slope} entries of the three axes
-    __shared__ RemapShared sh;
+    __shared__ RemapShared<SIO::kU8> sh;
     RemapPipe pipe(sm_remap);
     double *sm_tab = sm_remap + pipe_bytes(kRemapStages) / 8;
     if (threadIdx.x == 0) pipe.init();
@@ -625,6 +954,7 @@ __global__ void __launch_bounds__(kThreads, CT_MINB) remap_kernel(RemapArgs a) {
     const double *lut = a.lut + pair * CT_IDT_LUT_DOUBLES(bins);
     if (threadIdx.x < 9) sh.rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
     else if (threadIdx.x < 18 && next) sh.rot[threadIdx.x] = a.rot_next[pair * a.rot_stride + threadIdx.x - 9];
+    if (SIO::kU8) fill_decode(sh.dec_d, sh.dec_f, a.u8_as_f32);
     if (threadIdx.x >= 32 && threadIdx.x < 35) {
         const double *tail = lut + 9 * CT_IDT_EDGE_STRIDE(bins) + 4 * (threadIdx.x - 32);
         sh.grid[threadIdx.x - 32] = AxisGrid{tail[0], tail[1], tail[2], tail[3]};
@@ -665,26 +995,90 @@ int launch_keys_init(ct_context *h, int64_t *keys, int64_t n) {
     return CT_OK;
 }
 
-int launch_ranges(ct_context *h, const ct_batch *img, const double *rot, int64_t rot_stride, int n_rot,
-                  int64_t *keys, int64_t keys_stride, int32_t *status) {
-    CT_TRY(check_batch(h, img, "images"));
-    if (!rot || !keys) return fail(h, CT_E_INVALID, "rot/keys is NULL");
-    if (n_rot < 1) return fail(h, CT_E_INVALID, "n_rot must be >= 1");
-    const int chunk = n_rot == 1 ? 1 : CT_RANGES_CHUNK;
-    for (int k0 = 0; k0 < n_rot; k0 += chunk) {  // `chunk` rotations per pass over the image
-        const int n = n_rot - k0 < chunk ? n_rot - k0 : chunk;
-        RangesArgs a{img_of(img), src_kind(img), vec_ok(img), n, rot + 9 * k0, rot_stride, keys + CT_IDT_KEYS * k0, keys_stride, status};
-        if (chunk == 1) {
-            const int nblk = resident_blocks(h, ranges_kernel<1>, pipe_bytes(kRangesStages), img->npix, img->count);
-            ranges_kernel<1><<<dim3(nblk, img->count), kThreads, pipe_bytes(kRangesStages), h->stream>>>(a);
-        } else {
-            const int nblk = resident_blocks(h, ranges_kernel<CT_RANGES_CHUNK>, pipe_bytes(kRangesStages), img->npix, img->count);
-            ranges_kernel<CT_RANGES_CHUNK><<<dim3(nblk, img->count), kThreads, pipe_bytes(kRangesStages), h->stream>>>(a);
+template <typename IO, bool V, int N>
+static int launch_ranges_one(ct_context *h, const RangesArgs &a, int64_t npix, int count) {
+    constexpr int kRangesSmem = pipe_bytes(ranges_stages(N));
+    if (kRangesSmem > 48 * 1024) {
+        static bool raised[64] = {};
+        if (!raised[h->device & 63]) {
+            CT_CUDA(h, cudaFuncSetAttribute(ranges_kernel<IO, V, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRangesSmem));
+            raised[h->device & 63] = true;
         }
+    }
+    ranges_kernel<IO, V, N><<<dim3(resident_blocks(h, ranges_kernel<IO, V, N>, kRangesSmem, npix, count), count), kThreads,
+                              kRangesSmem, h->stream>>>(a);
+    return CT_OK;
+}
+
+// target (one rotation: iteration 0) and / or reference (n_rot_r rotations): per chunk of kMaxRot
+// reference rotations one K4a seed launch and one K4b launch; either image may be NULL.  With
+// init_keys the first seed launch also sets those keys to "+inf" (saves the keys_init launch).
+int launch_ranges_pair(ct_context *h, const ct_batch *target, const ct_batch *reference, int n_rot_r,
+                       const double *rot, int64_t rot_stride, int64_t *keys, int64_t keys_stride, int32_t *status,
+                       int64_t *init_keys, int64_t n_init) {
+    if (!target && !reference) return fail(h, CT_E_INVALID, "ranges needs at least one image");
+    if (target) CT_TRY(check_batch(h, target, "target"));
+    if (reference) CT_TRY(check_batch(h, reference, "reference"));
+    if (!rot || !keys) return fail(h, CT_E_INVALID, "rot/keys is NULL");
+    if (reference && n_rot_r < 1) return fail(h, CT_E_INVALID, "n_rot must be >= 1");
+    if (target && reference && target->count != reference->count) return fail(h, CT_E_INVALID, "batch counts differ");
+    const int count = target ? target->count : reference->count;
+    CT_TRY(ensure_seed(h, (size_t)count * 2 * kSeedCtas * 6 * kMaxRot));
+    for (int k0 = 0; k0 == 0 || (reference && k0 < n_rot_r); k0 += kMaxRot) {
+        RangesArgs a{};
+        const ct_batch *imgs[2] = {target && k0 == 0 ? target : nullptr, reference};
+        for (int z = 0; z < 2; ++z) {
+            if (!imgs[z]) continue;
+            a.img[z] = img_of(imgs[z]);
+            a.kind[z] = src_kind(imgs[z]);
+            a.vec[z] = vec_ok(imgs[z]);
+            a.u8_as_f32[z] = (imgs[z]->flags & CT_BATCH_U8_AS_F32) != 0;
+            a.n_rot[z] = z == 0 ? 1 : (n_rot_r - k0 < kMaxRot ? n_rot_r - k0 : kMaxRot);
+        }
+        a.rot = rot + 9 * k0;
+        a.rot_stride = rot_stride;
+        a.keys = keys + CT_IDT_KEYS * k0;
+        a.keys_stride = keys_stride;
+        a.status = status;
+        a.bound = h->ranges_bound;
+        a.seed = h->seed;
+        a.stats = h->ranges_stats;
+        if (k0 == 0) {
+            a.init_keys = init_keys;
+            a.n_init = n_init;
+        }
+        ranges_seed_kernel<<<dim3(kSeedCtas, count, 2), kThreads, 0, h->stream>>>(a);
         h->launches++;
         CT_CUDA(h, cudaGetLastError());
+        for (int z = 0; z < 2; ++z) {
+            if (!imgs[z]) continue;
+            a.which = z;
+            const int nr = a.n_rot[z] > 2 ? 4 : a.n_rot[z];   // instantiated widths: 1, 2, 4
+            const int64_t npix = imgs[z]->npix;
+            int rc = CT_OK;
+            switch (a.kind[z] * 2 + a.vec[z]) {
+#define CT_CASE(ID, T, L, V)                                                                  \
+    case ID:                                                                                  \
+        rc = nr == 1   ? launch_ranges_one<PixelIO<T, L>, V, 1>(h, a, npix, count)            \
+             : nr == 2 ? launch_ranges_one<PixelIO<T, L>, V, 2>(h, a, npix, count)            \
+                       : launch_ranges_one<PixelIO<T, L>, V, 4>(h, a, npix, count);           \
+        break;
+                CT_FOR_EACH_SRC(CT_CASE)
+#undef CT_CASE
+            }
+            CT_TRY(rc);
+            h->launches++;
+            CT_CUDA(h, cudaGetLastError());
+        }
     }
     return CT_OK;
+}
+
+int launch_ranges(ct_context *h, const ct_batch *img, const double *rot, int64_t rot_stride, int n_rot,
+                  int64_t *keys, int64_t keys_stride, int32_t *status) {
+    if (n_rot < 1) return fail(h, CT_E_INVALID, "n_rot must be >= 1");
+    if (n_rot == 1) return launch_ranges_pair(h, img, nullptr, 0, rot, rot_stride, keys, keys_stride, status, nullptr, 0);
+    return launch_ranges_pair(h, nullptr, img, n_rot, rot, rot_stride, keys, keys_stride, status, nullptr, 0);
 }
 
 static int check_stage(ct_context *h, const ct_idt_stage *s) {
@@ -732,17 +1126,21 @@ int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt
         a.img[z] = img_of(imgs[z]);
         a.kind[z] = src_kind(imgs[z]);
         a.vec[z] = vec_ok(imgs[z]);
+        a.u8_as_f32[z] = (imgs[z]->flags & CT_BATCH_U8_AS_F32) != 0;
         npix[z] = imgs[z]->npix;
     }
     const size_t smem = (size_t)kHistSmemFront + (size_t)((3 * s->bins) << copies_log2_for(s->bins)) * sizeof(unsigned int);
     // (the pipeline region alone is >= the 3*bins doubles the fused LUT build reuses)
+    const bool any_u8 = (imgs[0] && imgs[0]->dtype == CT_U8) || (imgs[1] && imgs[1]->dtype == CT_U8);
     if (smem > 48 * 1024 && !h->hist_smem_raised) {
-        CT_CUDA(h, cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+        CT_CUDA(h, cudaFuncSetAttribute(hist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+        CT_CUDA(h, cudaFuncSetAttribute(hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
         h->hist_smem_raised = true;
     }
     // one wave of resident CTAs per launch (persistent, tile-strided); every CTA serves both images
     int occ = 0;
-    CT_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hist_kernel, kThreads, smem));
+    if (any_u8) CT_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hist_kernel<true>, kThreads, smem));
+    else CT_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hist_kernel<false>, kThreads, smem));
     if (occ < 1) occ = 1;
     int64_t budget = ((int64_t)h->sm_count * occ) / B;
     const int64_t want = ((npix[0] > npix[1] ? npix[0] : npix[1]) / 2 + kThreads - 1) / kThreads;
@@ -764,7 +1162,8 @@ int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt
     CT_TRY(ensure_scratch(h, B));
     a.tickets = h->tickets;
     a.lut = lut_args(s, 0, trace, trace_iter, trace_niter);
-    hist_kernel<<<dim3(nblk, B), kThreads, smem, h->stream>>>(a);
+    if (any_u8) hist_kernel<true><<<dim3(nblk, B), kThreads, smem, h->stream>>>(a);
+    else hist_kernel<false><<<dim3(nblk, B), kThreads, smem, h->stream>>>(a);
     h->launches++;
     CT_CUDA(h, cudaGetLastError());
     return CT_OK;
@@ -786,7 +1185,6 @@ int launch_remap(ct_context *h, const ct_idt_stage *s, const ct_batch *dst, int 
     CT_TRY(check_batch(h, s->target, "target"));
     CT_TRY(check_batch(h, dst, "dst"));
     if (!s->rot || !s->lut) return fail(h, CT_E_INVALID, "rot/lut is NULL");
-    if (dst->dtype != CT_F64) return fail(h, CT_E_INVALID, "IDT state/output must be float64");
     if (dst->npix != s->target->npix || dst->count != s->target->count)
         return fail(h, CT_E_INVALID, "dst must have the target's npix and count");
     RemapArgs a{};
@@ -794,7 +1192,19 @@ int launch_remap(ct_context *h, const ct_idt_stage *s, const ct_batch *dst, int 
     a.dst = imgout_of(dst);
     a.kind = src_kind(s->target);
     a.vec = vec_ok(s->target) && vec_ok(dst);
-    a.dst_layout = dst->layout;
+    a.u8_as_f32 = (s->target->flags & CT_BATCH_U8_AS_F32) != 0;
+    a.clamp = (dst->flags & CT_BATCH_CLAMP01) != 0;
+    if (dst->dtype == CT_F64) {
+        a.dst_kind = dst->layout == CT_CHW ? kDstState : kDstF64;
+    } else {
+        // fused final conversion: only from the planar fp64 state (the last of n_iter >= 2 iterations)
+        const bool from_state = s->target->dtype == CT_F64 && s->target->layout == CT_CHW && a.vec;
+        if (!from_state) return fail(h, CT_E_UNSUPPORTED, "uint8 / float32 IDT output needs the planar float64 state as the source");
+        if (dst->dtype == CT_U8) a.dst_kind = dst->layout == CT_HWC ? kDstU8 : kDstU8Planar;
+        else if (dst->dtype == CT_F32 && dst->layout == CT_HWC) a.dst_kind = kDstF32;
+        else return fail(h, CT_E_UNSUPPORTED, "IDT output must be float64, uint8, or float32 CT_HWC");
+        if (s->rot_next || s->keys_next) return fail(h, CT_E_INVALID, "a converted output is final: rot_next / keys_next must be NULL");
+    }
     a.rot = s->rot;
     a.rot_next = s->rot_next;
     a.rot_stride = s->rot_stride;

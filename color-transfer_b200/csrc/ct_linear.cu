@@ -16,6 +16,7 @@ struct MomentsArgs {
     Img img[2];
     int kind[2];       // dtype*2 + layout
     int vec[2];
+    int u8_as_f32[2];
     int nimg;          // images per pair in this launch (1 or 2)
     int lab;
     double *partials;  // [B][nimg][gridDim.x][9]
@@ -91,10 +92,10 @@ __device__ __forceinline__ void accumulate_lab(const float (&rgbf)[N][3], double
 }
 
 template <typename IO, bool VEC, bool LAB>
-__device__ __forceinline__ void moments_image(const Img &im, int64_t pair, double (&acc)[9]) {
+__device__ __forceinline__ void moments_image(const Img &im, int64_t pair, const Decode &dec, double (&acc)[9]) {
     using T = typename IO::elem_t;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
-    constexpr int G = IO::G;
+    constexpr int G = IO::G, GS = IO::GS;
     const int64_t ngroups = im.npix / G;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -107,9 +108,12 @@ __device__ __forceinline__ void moments_image(const Img &im, int64_t pair, doubl
                 const bool more = g < ngroups;
                 typename IO::Raw next;
                 if (more) next = IO::template load_raw<VEC>(base, im.plane_stride, (int)g);
-                float xf[G][3];
-                IO::unpack_f(raw, xf);
-                accumulate_lab<G>(xf, acc);
+#pragma unroll
+                for (int q = 0; q < IO::NSUB; ++q) {
+                    float xf[GS][3];
+                    IO::unpack_sub_f(raw, q, dec, xf);
+                    accumulate_lab<GS>(xf, acc);
+                }
                 if (!more) break;
                 raw = next;
             }
@@ -117,16 +121,19 @@ __device__ __forceinline__ void moments_image(const Img &im, int64_t pair, doubl
     } else {
         for (; g < ngroups; g += stride) {
             const typename IO::Raw raw = IO::template load_raw<VEC>(base, im.plane_stride, (int)g);
-            double x[G][3];
-            IO::unpack(raw, x);
 #pragma unroll
-            for (int i = 0; i < G; ++i) accumulate_rgb(x[i], acc);
+            for (int q = 0; q < IO::NSUB; ++q) {
+                double x[GS][3];
+                IO::unpack_sub(raw, q, dec, x);
+#pragma unroll
+                for (int i = 0; i < GS; ++i) accumulate_rgb(x[i], acc);
+            }
         }
     }
     if (blockIdx.x == 0) {
         for (int64_t p = ngroups * G + threadIdx.x; p < im.npix; p += kThreads) {
             double x[3];
-            IO::load1(base, im.plane_stride, p, x);
+            IO::load1(base, im.plane_stride, p, dec, x);
             if (LAB) {
                 const float xf[1][3] = {{(float)x[0], (float)x[1], (float)x[2]}};
                 accumulate_lab<1>(xf, acc);
@@ -147,8 +154,15 @@ __global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_CTAS_PER_SM : 3) moment
 
     const Img im = a.img[z];
     const int sel = a.kind[z] * 2 + a.vec[z];
+    __shared__ double dec_d[256];
+    __shared__ float dec_f[256];
+    if (a.kind[z] >= 4) {   // uint8 image (block-uniform)
+        fill_decode(dec_d, dec_f, a.u8_as_f32[z]);
+        __syncthreads();
+    }
+    const Decode dec{dec_d, dec_f};
     switch (sel) {
-#define CT_CASE(ID, T, L, V) case ID: moments_image<PixelIO<T, L>, V, LAB>(im, pair, acc); break;
+#define CT_CASE(ID, T, L, V) case ID: moments_image<PixelIO<T, L>, V, LAB>(im, pair, dec, acc); break;
         CT_FOR_EACH_SRC(CT_CASE)
 #undef CT_CASE
     }
@@ -231,6 +245,8 @@ struct ApplyArgs {
     Img src;
     ImgOut dst;
     const double *xform;  // [B][16]
+    int u8_as_f32;        // uint8 source: decode k/255 in float32 (else float64)
+    int clamp;            // float output: clamp to [0,1]
 };
 
 template <bool LAB>
@@ -254,57 +270,66 @@ __device__ __forceinline__ void apply_pixel(const double *xf, const float *xff, 
 template <typename A, typename B> struct same_t { static constexpr bool value = false; };
 template <typename A> struct same_t<A, A> { static constexpr bool value = true; };
 
-template <typename SIO, typename DIO, bool VEC, bool LAB>
+// HYB32: the whole Lab chain in fp32 (float32 image in and out, or a uint8 frame decoded as float32:
+// Reinhard keeps the input dtype, linear.py:25-40)
+template <typename SIO, typename DIO, bool VEC, bool LAB, bool HYB32>
 __global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_APPLY_CTAS_PER_SM : CT_APPLY_CTAS_PER_SM) apply_kernel(ApplyArgs a) {
     using TS = typename SIO::elem_t;
     using TD = typename DIO::elem_t;
-    // float32 in and out (Reinhard keeps the input dtype, linear.py:25-40): the hybrid chain
-    constexpr bool HYB = LAB && same_t<TS, float>::value && same_t<TD, float>::value;
+    constexpr bool HYB = LAB && HYB32;
     const int64_t pair = blockIdx.y;
     __shared__ double xf[CT_XFORM_DOUBLES];
     __shared__ float xff[CT_XFORM_DOUBLES];
     __shared__ lab::ReinhardFold fold;
+    __shared__ double dec_d[SIO::kU8 ? 256 : 1];
+    __shared__ float dec_f[SIO::kU8 ? 256 : 1];
     if (threadIdx.x < CT_XFORM_DOUBLES) {
         xf[threadIdx.x] = a.xform[pair * CT_XFORM_DOUBLES + threadIdx.x];
         xff[threadIdx.x] = (float)xf[threadIdx.x];
     }
     if (HYB && threadIdx.x == 32) fold = lab::fold_reinhard(a.xform + pair * CT_XFORM_DOUBLES);
+    if (SIO::kU8) fill_decode(dec_d, dec_f, a.u8_as_f32);
     __syncthreads();
+    const Decode dec{dec_d, dec_f};
+    const bool clamp = a.clamp != 0;
     const TS *src = reinterpret_cast<const TS *>(a.src.data) + pair * a.src.image_stride;
     TD *dst = reinterpret_cast<TD *>(a.dst.data) + pair * a.dst.image_stride;
-    constexpr int G = SIO::G;
+    constexpr int G = SIO::G, GS = SIO::GS;
     const int64_t ngroups = a.src.npix / G;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += stride) {
         const typename SIO::Raw raw = SIO::template load_raw<VEC>(src, a.src.plane_stride, (int)g);
-        if (HYB) {
-            float xs[G][3], ys[G][3];
-            SIO::unpack_f(raw, xs);
-            lab::reinhard_group_h<G, CT_REINHARD_FMA_SEEDS>(fold, xs, ys);
-            DIO::template store<VEC, G>(dst, a.dst.plane_stride, g * G, ys);
-        } else {
-            double x[G][3], y[G][3];
-            float xs[G][3];
-            SIO::unpack(raw, x);
-            if (LAB) SIO::unpack_f(raw, xs);
 #pragma unroll
-            for (int i = 0; i < G; ++i) apply_pixel<LAB>(xf, xff, x[i], xs[i], y[i]);
-            DIO::template store<VEC, G>(dst, a.dst.plane_stride, g * G, y);
+        for (int q = 0; q < SIO::NSUB; ++q) {
+            if (HYB) {
+                float xs[GS][3], ys[GS][3];
+                SIO::unpack_sub_f(raw, q, dec, xs);
+                lab::reinhard_group_h<GS, CT_REINHARD_FMA_SEEDS>(fold, xs, ys);
+                DIO::template store<VEC, GS>(dst, a.dst.plane_stride, SIO::sub_pixel0(g, q), ys, clamp);
+            } else {
+                double x[GS][3], y[GS][3];
+                float xs[GS][3];
+                SIO::unpack_sub(raw, q, dec, x);
+                if (LAB) SIO::unpack_sub_f(raw, q, dec, xs);
+#pragma unroll
+                for (int i = 0; i < GS; ++i) apply_pixel<LAB>(xf, xff, x[i], xs[i], y[i]);
+                DIO::template store<VEC, GS>(dst, a.dst.plane_stride, SIO::sub_pixel0(g, q), y, clamp);
+            }
         }
     }
     if (blockIdx.x == 0) {
         for (int64_t p = ngroups * G + threadIdx.x; p < a.src.npix; p += kThreads) {
             double x[3], y[3];
-            SIO::load1(src, a.src.plane_stride, p, x);
+            SIO::load1(src, a.src.plane_stride, p, dec, x);
             const float xs[3] = {(float)x[0], (float)x[1], (float)x[2]};
             if (HYB) {
                 const float x1[1][3] = {{xs[0], xs[1], xs[2]}};
                 float y1[1][3];
                 lab::reinhard_group_h<1, CT_REINHARD_FMA_SEEDS>(fold, x1, y1);
-                DIO::store1(dst, a.dst.plane_stride, p, y1[0]);
+                DIO::store1(dst, a.dst.plane_stride, p, y1[0], clamp);
             } else {
                 apply_pixel<LAB>(xf, xff, x, xs, y);
-                DIO::store1(dst, a.dst.plane_stride, p, y);
+                DIO::store1(dst, a.dst.plane_stride, p, y, clamp);
             }
         }
     }
@@ -360,10 +385,12 @@ int launch_moments(ct_context *h, const ct_batch *a, const ct_batch *b, int lab,
     m.img[0] = img_of(a);
     m.kind[0] = src_kind(a);
     m.vec[0] = vec_ok(a);
+    m.u8_as_f32[0] = (a->flags & CT_BATCH_U8_AS_F32) != 0;
     if (b) {
         m.img[1] = img_of(b);
         m.kind[1] = src_kind(b);
         m.vec[1] = vec_ok(b);
+        m.u8_as_f32[1] = (b->flags & CT_BATCH_U8_AS_F32) != 0;
     }
     m.nimg = nimg;
     m.lab = lab;
@@ -390,15 +417,27 @@ int launch_solve(ct_context *h, int method, const double *sums_t, const double *
     return CT_OK;
 }
 
-template <typename SIO, bool LAB>
-static void launch_apply_dst(const ct_batch *out, bool vec, dim3 grid, cudaStream_t st, const ApplyArgs &a) {
-    if (out->dtype == CT_F32) {
-        if (vec) apply_kernel<SIO, PixelIO<float, CT_HWC>, true, LAB><<<grid, kThreads, 0, st>>>(a);
-        else apply_kernel<SIO, PixelIO<float, CT_HWC>, false, LAB><<<grid, kThreads, 0, st>>>(a);
+// HYB32 (all-fp32 Lab chain) when the image the reference would see is float32: a float32 source
+// with a float32 or uint8 destination, or a uint8 source decoded as float32.
+template <typename SIO, typename DIO, bool LAB>
+static void launch_apply_one(bool vec, bool hyb32, dim3 grid, cudaStream_t st, const ApplyArgs &a) {
+    if (LAB && hyb32) {
+        if (vec) apply_kernel<SIO, DIO, true, LAB, true><<<grid, kThreads, 0, st>>>(a);
+        else apply_kernel<SIO, DIO, false, LAB, true><<<grid, kThreads, 0, st>>>(a);
     } else {
-        if (vec) apply_kernel<SIO, PixelIO<double, CT_HWC>, true, LAB><<<grid, kThreads, 0, st>>>(a);
-        else apply_kernel<SIO, PixelIO<double, CT_HWC>, false, LAB><<<grid, kThreads, 0, st>>>(a);
+        if (vec) apply_kernel<SIO, DIO, true, LAB, false><<<grid, kThreads, 0, st>>>(a);
+        else apply_kernel<SIO, DIO, false, LAB, false><<<grid, kThreads, 0, st>>>(a);
     }
+}
+
+template <typename SIO, bool LAB>
+static int launch_apply_dst(ct_context *h, const ct_batch *out, bool vec, bool hyb32, dim3 grid, const ApplyArgs &a) {
+    cudaStream_t st = h->stream;
+    if (out->dtype == CT_F32 && out->layout == CT_HWC) launch_apply_one<SIO, PixelIO<float, CT_HWC>, LAB>(vec, hyb32, grid, st, a);
+    else if (out->dtype == CT_F64 && out->layout == CT_HWC) launch_apply_one<SIO, PixelIO<double, CT_HWC>, LAB>(vec, false, grid, st, a);
+    else if (out->dtype == CT_U8 && out->layout == CT_HWC) launch_apply_one<SIO, PixelIO<uint8_t, CT_HWC>, LAB>(vec, hyb32, grid, st, a);
+    else return fail(h, CT_E_UNSUPPORTED, "linear output must be float32 / float64 / uint8 CT_HWC");
+    return CT_OK;
 }
 
 int launch_apply(ct_context *h, int method, const ct_batch *target, const double *xform,
@@ -408,25 +447,31 @@ int launch_apply(ct_context *h, int method, const ct_batch *target, const double
     if (!xform) return fail(h, CT_E_INVALID, "xform is NULL");
     if (out->npix != target->npix || out->count != target->count)
         return fail(h, CT_E_INVALID, "out must have the target's npix and count");
-    if (out->layout != CT_HWC) return fail(h, CT_E_UNSUPPORTED, "linear output must be CT_HWC");
     const bool vec = vec_ok(target) && vec_ok(out);
-    const int group = target->dtype == CT_F32 ? 4 : 2;
+    const int group = target->dtype == CT_F32 ? 4 : (target->dtype == CT_U8 ? 16 : 2);
     const int nblk = blocks_for(h, target->npix, group, target->count, method == CT_REINHARD ? CT_LAB_APPLY_CTAS_PER_SM : CT_APPLY_CTAS_PER_SM,
                                 target->count == 1 ? 1 : (method == CT_REINHARD ? CT_APPLY_LAB_MIN_WAVES : CT_APPLY_MIN_WAVES));
     const dim3 grid(nblk, target->count);
-    ApplyArgs a{img_of(target), imgout_of(out), xform};
+    const bool u8f32 = (target->flags & CT_BATCH_U8_AS_F32) != 0;
+    ApplyArgs a{img_of(target), imgout_of(out), xform, u8f32 ? 1 : 0, (out->flags & CT_BATCH_CLAMP01) ? 1 : 0};
     const bool labm = method == CT_REINHARD;
+    // the dtype the reference would compute Reinhard in (linear.py:25-40 keeps the input float dtype)
+    const bool hyb32 = (target->dtype == CT_F32 || (target->dtype == CT_U8 && u8f32)) && out->dtype != CT_F64;
+    int rc = CT_OK;
     switch (src_kind(target)) {
-#define CT_APPLY(T, L)                                                                   \
-    if (labm) launch_apply_dst<PixelIO<T, L>, true>(out, vec, grid, h->stream, a);      \
-    else launch_apply_dst<PixelIO<T, L>, false>(out, vec, grid, h->stream, a);          \
+#define CT_APPLY(T, L)                                                                        \
+    rc = labm ? launch_apply_dst<PixelIO<T, L>, true>(h, out, vec, hyb32, grid, a)            \
+              : launch_apply_dst<PixelIO<T, L>, false>(h, out, vec, hyb32, grid, a);          \
     break;
         case 0: CT_APPLY(float, CT_HWC)
         case 1: CT_APPLY(float, CT_CHW)
         case 2: CT_APPLY(double, CT_HWC)
         case 3: CT_APPLY(double, CT_CHW)
+        case 4: CT_APPLY(uint8_t, CT_HWC)
+        case 5: CT_APPLY(uint8_t, CT_CHW)
 #undef CT_APPLY
     }
+    CT_TRY(rc);
     h->launches++;
     CT_CUDA(h, cudaGetLastError());
     return CT_OK;

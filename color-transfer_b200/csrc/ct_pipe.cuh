@@ -4,10 +4,12 @@
 // kStages x 12 KB per CTA are outstanding while every thread computes on 12 registers of raw
 // pixels, which is what lets these fp64-heavy kernels hide HBM latency at 2-3 CTAs per SM.
 //
-// A tile is kThreads pixel groups (1024 f32 pixels or 512 f64 pixels = 12 KB).  Interleaved
-// images need one bulk copy per tile, planar images three (one per channel plane).  Thread i then
-// reads its group with conflict-free 128-bit LDS (stride 48 B -> the 16 B bank groups 3i mod 8 of
-// a quarter warp are distinct; planar: stride 16 B).
+// A tile is kThreads pixel groups (1024 f32 pixels, 512 f64 pixels or 4096 uint8 pixels = 12 KB).
+// Interleaved images need one bulk copy per tile, planar images three (one per channel plane).
+// Thread i then reads its group with conflict-free 128-bit LDS (stride 48 B -> the 16 B bank groups
+// 3i mod 8 of a quarter warp are distinct; planar: stride 16 B).  A uint8 tile is four sub-tiles of
+// 1024 pixels; thread i takes pixels 4i..4i+3 of each (32-bit LDS at stride 12 B / 4 B: conflict
+// free), so that what it writes per sub-group is contiguous across the warp like a float tile.
 #pragma once
 
 #include "ct_common.cuh"
@@ -56,6 +58,17 @@ __device__ __forceinline__ float4 lds_vec<float4>(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+template <>
+__device__ __forceinline__ uint4 lds_vec<uint4>(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 template <>
 __device__ __forceinline__ double2 lds_vec<double2>(uint32_t addr) {
     double2 v;
@@ -86,10 +99,53 @@ struct Pipe {
     }
 };
 
-// Runs f(raw, first_pixel_of_group) on every pixel group of the FULL tiles first_tile, first_tile + tile_stride, ...
-// of one image; every thread of the CTA must call it (block-uniform trip count).  `pipe` must be
-// freshly initialised (phase 0) for each call.
-template <typename IO, typename P, typename F>
+// first pixel of sub-group s of this thread's group in a pipelined tile that starts at pixel t0
+template <typename IO>
+__device__ __forceinline__ int64_t pipe_sub_pixel0(int64_t t0, int s) {
+    return IO::kU8 ? t0 + s * (kThreads * IO::GS) + (int64_t)threadIdx.x * IO::GS : t0 + (int64_t)threadIdx.x * IO::G;
+}
+
+// byte offset of group gi (in [0, kThreads)) inside a stage
+template <typename IO>
+__device__ __forceinline__ uint32_t pipe_group_offset(uint32_t gi) {
+    if (IO::kU8) return IO::kLayout == CT_HWC ? 12u * gi : 4u * gi;
+    return IO::kLayout == CT_HWC ? 48u * gi : 16u * gi;
+}
+// one group of a stage -> registers; `src` = stage address + pipe_group_offset
+template <typename IO>
+__device__ __forceinline__ typename IO::Raw pipe_load_group(uint32_t src) {
+    constexpr int G = IO::G;
+    typename IO::Raw raw;
+    if (IO::kU8) {
+        uint32_t *w = reinterpret_cast<uint32_t *>(raw.e);
+        if (IO::kLayout == CT_HWC) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)      // sub-tile q: 3072 bytes, this thread's 12 bytes
+#pragma unroll
+                for (int k = 0; k < 3; ++k) w[3 * q + k] = lds_u32(src + q * (kTileBytes / 4) + 4 * k);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)      // plane c: 4096 bytes, sub-tile q: 1024 bytes
+#pragma unroll
+                for (int q = 0; q < 4; ++q) w[4 * c + q] = lds_u32(src + c * (kTileBytes / 3) + q * (kTileBytes / 12));
+        }
+    } else {
+        using V = typename IO::V;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            *reinterpret_cast<V *>(&raw.e[k * G]) = lds_vec<V>(src + (IO::kLayout == CT_HWC ? 16 * k : k * (kTileBytes / 3)));
+    }
+    return raw;
+}
+
+// Runs f(raw, first_pixel_of_tile) on this thread's pixel group of the FULL tiles first_tile,
+// first_tile + tile_stride, ... of one image (pipe_sub_pixel0 locates its sub-groups); every thread of
+// the CTA must call it (block-uniform trip count).  `pipe` must be freshly initialised (phase 0) for
+// each call.
+// SPLIT = 2: the two halves of the CTA do DIFFERENT work on the SAME pixels (K4 gives each half two of
+// the four rotations): every thread takes groups t % 128 and t % 128 + 128 of each tile and f is
+// called as f(raw, first_pixel_of_tile, u) for u = 0, 1.
+template <typename IO, int SPLIT = 1, typename P, typename F>
 __device__ __forceinline__ void pipe_for_each_group(P &pipe, const typename IO::elem_t *img, int64_t plane,
                                                     int ntiles, int first_tile, int tile_stride, F &&f) {
     using T = typename IO::elem_t;
@@ -110,28 +166,32 @@ __device__ __forceinline__ void pipe_for_each_group(P &pipe, const typename IO::
     };
     if (threadIdx.x == 0)
         for (int i = 0; i < kStages && i < mine; ++i) issue(i, i);
-    // this thread's group inside a stage
-    const uint32_t my_off = IO::kLayout == CT_HWC ? 48u * threadIdx.x : 16u * threadIdx.x;
+    // this thread's group(s) inside a stage
+    uint32_t my_off[SPLIT];
+#pragma unroll
+    for (int u = 0; u < SPLIT; ++u)
+        my_off[u] = pipe_group_offset<IO>(SPLIT == 1 ? threadIdx.x : (threadIdx.x % (kThreads / SPLIT)) + u * (kThreads / SPLIT));
     int s = 0;
     uint32_t parity = 0;
     for (int i = 0; i < mine; ++i) {
         const uint32_t full = pipe.full + 8 * s, empty = pipe.empty + 8 * s;
         mbar_wait(full, parity);
-        typename IO::Raw raw;
-        {
-            using V = typename IO::V;
-            const uint32_t src = pipe.stage + s * kTileBytes + my_off;
+        typename IO::Raw raw[SPLIT];
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                *reinterpret_cast<V *>(&raw.e[k * G]) = lds_vec<V>(src + (IO::kLayout == CT_HWC ? 16 * k : k * (kTileBytes / 3)));
-        }
+        for (int u = 0; u < SPLIT; ++u) raw[u] = pipe_load_group<IO>(pipe.stage + s * kTileBytes + my_off[u]);
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(empty);  // this warp has copied its groups out
         if (threadIdx.x == 0 && i + kStages < mine) {
             mbar_wait(empty, parity);  // all 8 warps are done with the stage
             issue(i + kStages, s);
         }
-        f(raw, (int64_t)(first_tile + (int64_t)i * tile_stride) * kTilePx + (int64_t)threadIdx.x * G);
+        const int64_t tile0 = (int64_t)(first_tile + (int64_t)i * tile_stride) * kTilePx;
+        if constexpr (SPLIT == 1) {
+            f(raw[0], tile0);
+        } else {
+#pragma unroll
+            for (int u = 0; u < SPLIT; ++u) f(raw[u], tile0, u);
+        }
         if (++s == kStages) {
             s = 0;
             parity ^= 1u;

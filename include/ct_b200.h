@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CT_ABI_VERSION 1
+#define CT_ABI_VERSION 2
 
 typedef struct ct_context *ct_handle;
 
@@ -43,7 +43,7 @@ typedef enum ct_status {
     CT_E_NOMEM = -7        /* workspace too small / allocation failed                             */
 } ct_status;
 
-enum { CT_F32 = 0, CT_F64 = 1 };
+enum { CT_F32 = 0, CT_F64 = 1, CT_U8 = 2 };
 enum { CT_HWC = 0, CT_CHW = 1 };
 
 /* Which closed-form transfer (ref: methods/linear.py). */
@@ -62,10 +62,21 @@ typedef struct ct_batch {
     int64_t image_stride; /* elements between consecutive images (ignored when count == 1)     */
     int64_t plane_stride; /* CT_CHW: elements between channel planes (0 means npix)            */
     int32_t count;        /* B                                                                 */
-    int32_t dtype;        /* CT_F32 | CT_F64                                                   */
+    int32_t dtype;        /* CT_F32 | CT_F64 | CT_U8                                           */
     int32_t layout;       /* CT_HWC | CT_CHW                                                   */
-    int32_t reserved;
+    int32_t flags;        /* CT_BATCH_* bits, 0 by default                                     */
 } ct_batch;
+
+/* uint8 images (video frames, torchvision read_image tensors) are decoded INSIDE the kernels that
+ * read them and, as outputs, encoded inside the kernel that writes them - no conversion pass:
+ *   input : x = k / 255 exactly as the reference's loaders produce it - float64 (skimage.img_as_float,
+ *           ref: utils/postprocess.py:138) or, with CT_BATCH_U8_AS_F32, float32 (torch `/ 255`,
+ *           ref: utils/data.py:106).  The transfer then runs as if the caller had passed that float image.
+ *   output: np.rint(np.clip(y, 0, 1) * 255) (img_as_ubyte of the clipped result, ref:
+ *           utils/postprocess.py:138).
+ * CT_BATCH_CLAMP01 on a float output applies torch.clamp(y, 0, 1) (ref: methods/__init__.py:30). */
+#define CT_BATCH_U8_AS_F32 1
+#define CT_BATCH_CLAMP01 2
 
 /* ------------------------------------------------------------------ handle */
 int ct_abi_version(void);
