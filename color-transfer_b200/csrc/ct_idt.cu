@@ -165,7 +165,6 @@ __global__ void keys_init_kernel(int64_t *keys, int64_t n) {
 #define CT_SEED_FRACTION 128   // K4a samples one pixel in this many
 #endif
 constexpr int kMaxRot = 4;     // most rotations one pass can take
-constexpr int kSeedCtas = 32;  // seed CTAs (partial results) per image
 constexpr int kSeedRun = 8;    // consecutive pixels per sampled run
 
 struct RangesArgs {
@@ -179,7 +178,7 @@ struct RangesArgs {
     int64_t keys_stride;
     int32_t *status;
     float bound;     // screen validity bound on |x0|+|x1|+|x2| (pixels beyond it take the exact path)
-    long long *seed; // [B][2][kSeedCtas][6 * kMaxRot] keys of the subsample's extremes (K4a -> K4b)
+    long long *seed; // [B][2][6 * kMaxRot] keys of the subsample's extremes (K4a -> K4b), kSeedEmpty where none
     int64_t *init_keys;   // K4a also sets these n_init keys to "+inf" (what keys_init_kernel does)
     int64_t n_init;
     unsigned long long *stats;  // optional diagnostics: [0] pixels sent to the exact path, [1] flagged repeats skipped
@@ -191,11 +190,16 @@ __device__ __forceinline__ int64_t seed_samples(int64_t npix) {
     return want < npix ? want : npix;
 }
 
-// K4a.  grid (kSeedCtas, B, 2): exact ranges of the subsample of image z of pair y; CTA 0 of the whole
-// grid also initialises the pair's range keys.
-__global__ void __launch_bounds__(kThreads, 2) ranges_seed_kernel(RangesArgs a) {
+// K4a.  grid (seed CTAs, B, 2): exact ranges of the subsample of image z of pair y, folded into
+// seed[pair][z][6 * kMaxRot] with integer atomic minima (the host presets the array to kSeedEmpty);
+// the grid also initialises the pair's range keys.  Every thread loads four samples once (all in
+// flight together) and evaluates every rotation on them.
+constexpr long long kSeedEmpty = 0x7f7f7f7f7f7f7f7fLL;   // what cudaMemsetAsync(0x7f) leaves: the key of 1.38e306; a sample
+                                                         // that really had it would only make the pass run unseeded
+
+__global__ void __launch_bounds__(kThreads) ranges_seed_kernel(RangesArgs a) {
     __shared__ double rot[9 * kMaxRot];
-    __shared__ double red[kWarps][6 * kMaxRot];
+    __shared__ long long best[6 * kMaxRot];
     __shared__ double dec_d[256];
     __shared__ float dec_f[256];
     const int z = blockIdx.z;
@@ -208,64 +212,62 @@ __global__ void __launch_bounds__(kThreads, 2) ranges_seed_kernel(RangesArgs a) 
     const int n_rot = a.n_rot[z];
     if (!n_rot) return;
     if (threadIdx.x < 9 * n_rot) rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
-    fill_decode(dec_d, dec_f, a.u8_as_f32[z]);
+    if (threadIdx.x < 6 * kMaxRot) best[threadIdx.x] = kSeedEmpty;
+    if (a.kind[z] >= 4) fill_decode(dec_d, dec_f, a.u8_as_f32[z]);
     __syncthreads();
     const Decode dec{dec_d, dec_f};
     const Img &im = a.img[z];
     const int64_t nsamp = seed_samples(im.npix), step = im.npix / nsamp;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // one rotation at a time (12 running extrema in registers); the sample is re-read from L2
-    for (int k = 0; k < n_rot; ++k) {
-        double mn[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) mn[i] = i < 3 ? INFINITY : -INFINITY;
-        bool bad = false;
-        auto sample = [&](auto io) {
+    const int lane = threadIdx.x & 31;
+    // runs of kSeedRun pixels, one per cell of kSeedRun * step pixels, at a hashed offset inside the
+    // cell (a fixed offset would alias with the row length and sample only a few image columns)
+    const int64_t cell = kSeedRun * step, slack = cell - kSeedRun + 1;
+    // block-uniform trip count: the warp shuffles below need every lane
+    for (int64_t b0 = (int64_t)blockIdx.x * (4 * kThreads); b0 < nsamp; b0 += (int64_t)gridDim.x * (4 * kThreads)) {
+        const int64_t i0 = b0 + threadIdx.x;
+        double x[4][3];
+        bool have[4];
+        auto load = [&](auto io) {
             using IO = decltype(io);
             using T = typename IO::elem_t;
             const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
-            // runs of kSeedRun pixels, one per cell of kSeedRun * step pixels, at a hashed offset inside the
-            // cell (a fixed offset would alias with the row length and sample only a few image columns)
-            const int64_t cell = kSeedRun * step, slack = cell - kSeedRun + 1;
-            for (int64_t i0 = (int64_t)blockIdx.x * kThreads + threadIdx.x; i0 < nsamp; i0 += 4 * (int64_t)gridDim.x * kThreads) {
-                double x[4][3];
-                bool have[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {   // four independent loads in flight per thread
-                    const int64_t i = i0 + u * (int64_t)gridDim.x * kThreads;
-                    const int64_t run = i / kSeedRun;
-                    const int64_t jitter = step == 1 ? 0 : (int64_t)(((uint32_t)run * 2654435761u) >> 8) % slack;
-                    const int64_t p = run * cell + jitter + (i % kSeedRun);
-                    have[u] = i < nsamp && p < im.npix;
-                    if (have[u]) IO::load1(base, im.plane_stride, p, dec, x[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (have[u]) track_range<false>(rot + 9 * k, x[u], mn, bad);
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + u * kThreads;
+                const int64_t run = i / kSeedRun;
+                const int64_t jitter = step == 1 ? 0 : (int64_t)(((uint32_t)run * 2654435761u) >> 8) % slack;
+                const int64_t p = run * cell + jitter + (i % kSeedRun);
+                have[u] = i < nsamp && p < im.npix;
+                if (have[u]) IO::load1(base, im.plane_stride, p, dec, x[u]);
             }
         };
         switch (a.kind[z]) {
-            case 0: sample(PixelIO<float, CT_HWC>{}); break;
-            case 1: sample(PixelIO<float, CT_CHW>{}); break;
-            case 2: sample(PixelIO<double, CT_HWC>{}); break;
-            case 3: sample(PixelIO<double, CT_CHW>{}); break;
-            case 4: sample(PixelIO<uint8_t, CT_HWC>{}); break;
-            default: sample(PixelIO<uint8_t, CT_CHW>{}); break;
+            case 0: load(PixelIO<float, CT_HWC>{}); break;
+            case 1: load(PixelIO<float, CT_CHW>{}); break;
+            case 2: load(PixelIO<double, CT_HWC>{}); break;
+            case 3: load(PixelIO<double, CT_CHW>{}); break;
+            case 4: load(PixelIO<uint8_t, CT_HWC>{}); break;
+            default: load(PixelIO<uint8_t, CT_CHW>{}); break;
         }
+        for (int k = 0; k < n_rot; ++k) {
+            double mn[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const double v = warp_min(i < 3 ? mn[i] : -mn[i]);   // min p, min -p
-            if (lane == 0) red[warp][6 * k + i] = v;
+            for (int i = 0; i < 6; ++i) mn[i] = i < 3 ? INFINITY : -INFINITY;
+            bool bad = false;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (have[u]) track_range<false>(rot + 9 * k, x[u], mn, bad);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const double v = warp_min(i < 3 ? mn[i] : -mn[i]);   // min p, min -p
+                // a NaN sample is never smaller; an infinite one leaves +-inf: the main pass then flags every pixel
+                if (lane == 0 && v < INFINITY) atomicMin(&best[6 * k + i], (long long)key_of(v));
+            }
         }
     }
     __syncthreads();
-    if (threadIdx.x < 6 * n_rot) {
-        double v = red[0][threadIdx.x];
-#pragma unroll
-        for (int w = 1; w < kWarps; ++w) v = fmin(v, red[w][threadIdx.x]);
-        // a NaN / inf sample leaves +-inf here: the main pass then flags every pixel (and reports it)
-        a.seed[((pair * 2 + z) * kSeedCtas + blockIdx.x) * (6 * kMaxRot) + threadIdx.x] = (long long)key_of(v);
-    }
+    if (threadIdx.x < 6 * n_rot && best[threadIdx.x] != kSeedEmpty)
+        atomicMin(a.seed + (pair * 2 + z) * (6 * kMaxRot) + threadIdx.x, best[threadIdx.x]);
 }
 
 struct RangesShared {
@@ -470,17 +472,13 @@ __global__ void __launch_bounds__(kThreads, NROT == 1 ? CT_RANGES_MINB1 : CT_RAN
     }
     if (IO::kU8) fill_decode(dec_d, dec_f, a.u8_as_f32[z]);
     if (threadIdx.x < 9 * n_rot) sh.rot[threadIdx.x] = a.rot[pair * a.rot_stride + threadIdx.x];
-    if (threadIdx.x < 6 * kMaxRot) (&sh.key[0][0])[threadIdx.x] = (long long)kKeyPlusInf;
-    __syncthreads();
-    {   // the subsample's extremes: kSeedCtas partial results per key
-        const long long *sd = a.seed + (pair * 2 + z) * kSeedCtas * (6 * kMaxRot);
-        for (int i = threadIdx.x; i < kSeedCtas * 6 * kMaxRot; i += kThreads) {
-            const int t = i % (6 * kMaxRot);
-            if (t < 6 * n_rot) {
-                const long long w = __ldcg(sd + i);
-                if (w < (long long)kKeyPlusInf) atomicMin(&(&sh.key[0][0])[t], w);
-            }
+    if (threadIdx.x < 6 * kMaxRot) {   // the subsample's extremes
+        long long v = (long long)kKeyPlusInf;
+        if (threadIdx.x < 6 * n_rot) {
+            const long long w = __ldcg(a.seed + (pair * 2 + z) * (6 * kMaxRot) + threadIdx.x);
+            if (w != kSeedEmpty) v = w;
         }
+        (&sh.key[0][0])[threadIdx.x] = v;
     }
     __syncthreads();
     if (threadIdx.x < 3 * n_rot) {
@@ -1023,7 +1021,7 @@ int launch_ranges_pair(ct_context *h, const ct_batch *target, const ct_batch *re
     if (reference && n_rot_r < 1) return fail(h, CT_E_INVALID, "n_rot must be >= 1");
     if (target && reference && target->count != reference->count) return fail(h, CT_E_INVALID, "batch counts differ");
     const int count = target ? target->count : reference->count;
-    CT_TRY(ensure_seed(h, (size_t)count * 2 * kSeedCtas * 6 * kMaxRot));
+    CT_TRY(ensure_seed(h, (size_t)count * 2 * 6 * kMaxRot));
     for (int k0 = 0; k0 == 0 || (reference && k0 < n_rot_r); k0 += kMaxRot) {
         RangesArgs a{};
         const ct_batch *imgs[2] = {target && k0 == 0 ? target : nullptr, reference};
@@ -1047,7 +1045,13 @@ int launch_ranges_pair(ct_context *h, const ct_batch *target, const ct_batch *re
             a.init_keys = init_keys;
             a.n_init = n_init;
         }
-        ranges_seed_kernel<<<dim3(kSeedCtas, count, 2), kThreads, 0, h->stream>>>(a);
+        int64_t npix_max = 0;
+        for (int z = 0; z < 2; ++z)
+            if (imgs[z] && imgs[z]->npix > npix_max) npix_max = imgs[z]->npix;
+        int64_t seed_ctas = (npix_max / CT_SEED_FRACTION + 4 * kThreads - 1) / (4 * kThreads);
+        seed_ctas = seed_ctas < 4 ? 4 : (seed_ctas > 1024 ? 1024 : seed_ctas);
+        CT_CUDA(h, cudaMemsetAsync(h->seed, 0x7f, sizeof(long long) * (size_t)count * 2 * 6 * kMaxRot, h->stream));
+        ranges_seed_kernel<<<dim3((unsigned)seed_ctas, count, 2), kThreads, 0, h->stream>>>(a);
         h->launches++;
         CT_CUDA(h, cudaGetLastError());
         for (int z = 0; z < 2; ++z) {
