@@ -15,7 +15,8 @@ LIB_PATH = os.environ.get("CT_B200_LIB") or os.path.join(_HERE, "libct_b200.so")
 
 CT_OK, CT_E_INVALID, CT_E_CUDA, CT_E_NONFINITE, CT_E_NOT_PD, CT_E_SINGULAR, CT_E_UNSUPPORTED, CT_E_NOMEM = (
     0, -1, -2, -3, -4, -5, -6, -7)
-CT_F32, CT_F64 = 0, 1
+CT_F32, CT_F64, CT_U8 = 0, 1, 2
+CT_BATCH_U8_AS_F32, CT_BATCH_CLAMP01 = 1, 2   # ct_batch.flags
 CT_HWC, CT_CHW = 0, 1
 CT_REINHARD, CT_CCS, CT_MKL_MK, CT_MKL_SQRT, CT_MKL_CHOLESKY = 0, 1, 2, 3, 4
 CT_MOMENT_DOUBLES = 10
@@ -119,7 +120,7 @@ class CtError(RuntimeError):
         self.message = message
 
 
-_DTYPES = {np.dtype(np.float32): CT_F32, np.dtype(np.float64): CT_F64}
+_DTYPES = {np.dtype(np.float32): CT_F32, np.dtype(np.float64): CT_F64, np.dtype(np.uint8): CT_U8}
 
 
 def batch_from_pointer(ptr, npix, dtype, layout=CT_HWC, count=1, image_stride=0, plane_stride=0):

@@ -90,6 +90,12 @@ int ensure_stage(ct_context *h, size_t bytes) {
 
 int ensure_seed(ct_context *h, size_t words) { return grow(h, &h->seed, &h->seed_words, words, false); }
 
+// the float type the reference would see: a uint8 frame is what its loader decodes it to
+static int decoded_dtype(const ct_batch *b) {
+    if (b->dtype == CT_U8) return (b->flags & CT_BATCH_U8_AS_F32) ? CT_F32 : CT_F64;
+    return b->dtype;
+}
+
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct Carver {
@@ -142,7 +148,11 @@ static int idt_run(ct_context *h, const ct_batch *target, const ct_batch *refere
     if (bins > CT_IDT_MAX_BINS) return fail(h, CT_E_UNSUPPORTED, "bins=%d exceeds CT_IDT_MAX_BINS=%d", bins, CT_IDT_MAX_BINS);
     if (reference->count != target->count || out->count != target->count) return fail(h, CT_E_INVALID, "batch counts differ");
     if (out->npix != target->npix) return fail(h, CT_E_INVALID, "out.npix != target.npix");
-    if (out->dtype != CT_F64 || out->layout != CT_HWC) return fail(h, CT_E_INVALID, "IDT output must be float64 CT_HWC");
+    const bool out_f64 = out->dtype == CT_F64 && out->layout == CT_HWC;
+    const bool out_fused = (out->dtype == CT_U8) || (out->dtype == CT_F32 && out->layout == CT_HWC);   // converted inside the last K7
+    if (!out_f64 && !out_fused) return fail(h, CT_E_INVALID, "IDT output must be float64 CT_HWC, float32 CT_HWC or uint8");
+    if (out_fused && n_iter < 2)
+        return fail(h, CT_E_UNSUPPORTED, "uint8 / float32 IDT output needs n_iter >= 2 (it is written by the last iteration from the float64 state)");
     const int B = target->count;
     const size_t need = idt_layout(nullptr, target->npix, B, bins, n_iter).bytes;
     if (!workspace) {
@@ -186,7 +196,7 @@ static int idt_run(ct_context *h, const ct_batch *target, const ct_batch *refere
         s.status = st;
         s.bins = bins;
         CT_TRY(launch_hist(h, &s, 1, trace, it, n_iter));
-        CT_TRY(launch_remap(h, &s, last ? out : &state, it == 0 && target->dtype == CT_F32));
+        CT_TRY(launch_remap(h, &s, last ? out : &state, it == 0 && decoded_dtype(target) == CT_F32));
     }
     return CT_OK;
 }
@@ -411,7 +421,7 @@ int ct_ssim(ct_handle h, const float *x, const float *y, int32_t count, int32_t 
 // Host pipeline shared by the two *_host entry points: per pair H2D on copy_in, kernels on the
 // handle's stream, D2H on copy_out, two slots in flight.
 namespace {
-constexpr int kSlots = 2;
+constexpr int kSlots = 3;   // pairs in flight: H2D of pair b+1 / b+2 and D2H of pair b-1 overlap the kernels of pair b
 struct Pipeline {
     cudaEvent_t in_ready[kSlots], done[kSlots], out_free[kSlots];
     bool ok = false;
@@ -455,7 +465,7 @@ int run_host_pipeline(ct_context *h, const ct_batch *target, const ct_batch *ref
                       size_t extra_ws, Launch &&launch) {
     const int B = target->count;
     const size_t tb = align_up(image_bytes(target)), rb = align_up(image_bytes(reference)), ob = align_up(image_bytes(out));
-    const int slots = B > 1 ? kSlots : 1;
+    const int slots = B > 1 ? (B < kSlots ? B : kSlots) : 1;
     CT_TRY(ensure_stage(h, (tb + rb + ob) * slots + extra_ws));
     Pipeline pl;
     if (pl.init() != 0) return fail(h, CT_E_CUDA, "event creation failed");
@@ -504,39 +514,34 @@ int run_host_pipeline(ct_context *h, const ct_batch *target, const ct_batch *ref
     return CT_OK;
 }
 
-// uint8 frames: [H2D u8 pair] -> u8_to_float x2 -> launch(float pair -> float out) -> float_to_u8 -> [D2H u8]
-// with the same three-stream, two-slot overlap.  `in_dtype` is the float type the frames are
-// decoded to (the semantics of the reference loader being replaced), `out_dtype` what the
-// transfer produces before quantisation.
+// uint8 frames: [H2D u8 pair] -> launch(u8 pair -> u8 out) -> [D2H u8] with the same three-stream overlap.
+// The kernels decode the frames as they read them and encode the result as they write it
+// (CT_U8 batches): 3 bytes per pixel cross PCIe each way and there is no conversion pass.
 template <typename Launch>
 int run_host_pipeline_u8(ct_context *h, const uint8_t *target, const uint8_t *reference, uint8_t *out, int count,
-                         int64_t npix_t, int64_t npix_r, int in_dtype, int out_dtype, Launch &&launch) {
+                         int64_t npix_t, int64_t npix_r, int as_float32, Launch &&launch) {
     const size_t nt = (size_t)npix_t * 3, nr = (size_t)npix_r * 3;
     const size_t ut = align_up(nt), ur = align_up(nr), uo = align_up(nt);
-    const size_t ft = align_up(nt * elem_size(in_dtype)), fr = align_up(nr * elem_size(in_dtype)), fo = align_up(nt * elem_size(out_dtype));
-    const size_t slot = ut + ur + uo + ft + fr + fo;
-    const int slots = count > 1 ? kSlots : 1;
+    const size_t slot = ut + ur + uo;
+    const int slots = count > 1 ? (count < kSlots ? count : kSlots) : 1;
     CT_TRY(ensure_stage(h, slot * slots));
     Pipeline pl;
     if (pl.init() != 0) return fail(h, CT_E_CUDA, "event creation failed");
     unsigned char *base = static_cast<unsigned char *>(h->stage);
+    const int flags = as_float32 ? CT_BATCH_U8_AS_F32 : 0;
     for (int b = 0; b < count; ++b) {
         const int s = b % slots;
         unsigned char *p = base + (size_t)s * slot;
         uint8_t *d_ut = p, *d_ur = p + ut, *d_uo = p + ut + ur;
-        unsigned char *d_ft = p + ut + ur + uo, *d_fr = d_ft + ft, *d_fo = d_fr + fr;
         if (b >= slots) CT_CUDA(h, cudaStreamWaitEvent(h->copy_in, pl.done[s], 0));
         CT_CUDA(h, cudaMemcpyAsync(d_ut, target + (size_t)b * nt, nt, cudaMemcpyHostToDevice, h->copy_in));
         CT_CUDA(h, cudaMemcpyAsync(d_ur, reference + (size_t)b * nr, nr, cudaMemcpyHostToDevice, h->copy_in));
         CT_CUDA(h, cudaEventRecord(pl.in_ready[s], h->copy_in));
         CT_CUDA(h, cudaStreamWaitEvent(h->stream, pl.in_ready[s], 0));
         if (b >= slots) CT_CUDA(h, cudaStreamWaitEvent(h->stream, pl.out_free[s], 0));
-        CT_TRY(launch_u8_to_float(h, d_ut, d_ft, in_dtype, (int64_t)nt));
-        CT_TRY(launch_u8_to_float(h, d_ur, d_fr, in_dtype, (int64_t)nr));
-        ct_batch t1{d_ft, npix_t, 0, 0, 1, in_dtype, CT_HWC, 0}, r1{d_fr, npix_r, 0, 0, 1, in_dtype, CT_HWC, 0};
-        ct_batch o1{d_fo, npix_t, 0, 0, 1, out_dtype, CT_HWC, 0};
+        ct_batch t1{d_ut, npix_t, 0, 0, 1, CT_U8, CT_HWC, flags}, r1{d_ur, npix_r, 0, 0, 1, CT_U8, CT_HWC, flags};
+        ct_batch o1{d_uo, npix_t, 0, 0, 1, CT_U8, CT_HWC, 0};
         CT_TRY(launch(b, &t1, &r1, &o1));
-        CT_TRY(launch_float_to_u8(h, d_fo, out_dtype, d_uo, (int64_t)nt));
         CT_CUDA(h, cudaEventRecord(pl.done[s], h->stream));
         CT_CUDA(h, cudaStreamWaitEvent(h->copy_out, pl.done[s], 0));
         CT_CUDA(h, cudaMemcpyAsync(out + (size_t)b * nt, d_uo, nt, cudaMemcpyDeviceToHost, h->copy_out));
@@ -593,9 +598,7 @@ int ct_linear_transfer_host_u8(ct_handle h, int method, const uint8_t *target, c
         return fail(h, CT_E_INVALID, "bad uint8 batch arguments");
     CT_TRY(ensure_scratch(h, count));
     CT_CUDA(h, cudaMemsetAsync(h->status, 0, sizeof(int) * (size_t)count, h->stream));
-    const int in_dtype = as_float32 ? CT_F32 : CT_F64;
-    const int out_dtype = method == CT_REINHARD ? in_dtype : CT_F64;   // the reference's dtype flow
-    CT_TRY(run_host_pipeline_u8(h, target, reference, out, count, npix_target, npix_reference, in_dtype, out_dtype,
+    CT_TRY(run_host_pipeline_u8(h, target, reference, out, count, npix_target, npix_reference, as_float32,
                                 [&](int b, const ct_batch *t, const ct_batch *r, const ct_batch *o) {
                                     CT_TRY(launch_moments(h, t, r, method == CT_REINHARD, h->sums + (size_t)b * 2 * CT_MOMENT_DOUBLES,
                                                           method, h->xform + (size_t)b * CT_XFORM_DOUBLES, h->status + b));
@@ -615,15 +618,23 @@ int ct_idt_transfer_host_u8(ct_handle h, const uint8_t *target, const uint8_t *r
     CT_TRY(ensure_scratch(h, count));
     const size_t rot_bytes = align_up(sizeof(double) * (size_t)count * n_iter * 9);
     const size_t idt_ws = idt_layout(nullptr, npix_target, 1, bins, n_iter).bytes;
-    CT_TRY(ensure_ws(h, rot_bytes + idt_ws));
+    const size_t tmp_bytes = n_iter < 2 ? align_up(sizeof(double) * 3 * (size_t)npix_target) : 0;
+    CT_TRY(ensure_ws(h, rot_bytes + idt_ws + tmp_bytes));
     double *d_rot = static_cast<double *>(h->ws);
     void *idt_base = static_cast<unsigned char *>(h->ws) + rot_bytes;
+    h->u8_tmp = reinterpret_cast<double *>(static_cast<unsigned char *>(h->ws) + rot_bytes + idt_ws);
     CT_CUDA(h, cudaMemcpyAsync(d_rot, rotations, sizeof(double) * (size_t)count * n_iter * 9, cudaMemcpyHostToDevice, h->stream));
     CT_CUDA(h, cudaMemsetAsync(h->status, 0, sizeof(int) * (size_t)count, h->stream));
-    CT_TRY(run_host_pipeline_u8(h, target, reference, out, count, npix_target, npix_reference, as_float32 ? CT_F32 : CT_F64, CT_F64,
+    CT_TRY(run_host_pipeline_u8(h, target, reference, out, count, npix_target, npix_reference, as_float32,
                                 [&](int b, const ct_batch *t, const ct_batch *r, const ct_batch *o) {
-                                    return idt_run(h, t, r, o, d_rot + (size_t)b * n_iter * 9, bins, n_iter, idt_base, idt_ws,
-                                                   nullptr, h->status + b);
+                                    if (n_iter >= 2)
+                                        return idt_run(h, t, r, o, d_rot + (size_t)b * n_iter * 9, bins, n_iter, idt_base, idt_ws,
+                                                       nullptr, h->status + b);
+                                    // a single iteration has no float64 state to convert from: float64 result, then encode
+                                    ct_batch f{h->u8_tmp, t->npix, 0, 0, 1, CT_F64, CT_HWC, 0};
+                                    CT_TRY(idt_run(h, t, r, &f, d_rot + (size_t)b * n_iter * 9, bins, n_iter, idt_base, idt_ws,
+                                                   nullptr, h->status + b));
+                                    return launch_float_to_u8(h, h->u8_tmp, CT_F64, static_cast<uint8_t *>(o->data), 3 * t->npix);
                                 }));
     return first_bad_status(h, h->status, count);
 }

@@ -31,6 +31,7 @@ struct ct_context {
     size_t ws_bytes = 0;
     void *stage = nullptr;
     size_t stage_bytes = 0;
+    double *u8_tmp = nullptr;   // inside ws: float64 result of a one-iteration IDT on uint8 frames before it is encoded
 
     // K4 screen: pixels with |x0|+|x1|+|x2| above this take the exact fp64 path (CT_RANGES_BOUND)
     float ranges_bound = 16.0f;

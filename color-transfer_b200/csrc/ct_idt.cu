@@ -183,6 +183,7 @@ struct RangesArgs {
     int64_t n_init;
     unsigned long long *stats;  // optional diagnostics: [0] pixels sent to the exact path, [1] flagged repeats skipped
     int which;       // K4b: the image slot this launch streams
+    uint32_t zero;   // always 0 (ct_pipe.cuh: pipe_for_each_group)
 };
 
 __device__ __forceinline__ int64_t seed_samples(int64_t npix) {
@@ -358,7 +359,7 @@ struct KnownPixels {
 // state per thread (24 instead of 48 registers), which is what lets three CTAs share an SM.
 template <typename IO, bool VEC, int NROT, int SPLIT, typename RangesPipe>
 __device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, RangesShared &sh, const Decode &dec, int n_rot,
-                                             float bound, RangesPipe &pipe, int first_block, int nblocks, bool stats) {
+                                             float bound, RangesPipe &pipe, int first_block, int nblocks, bool stats, uint32_t zero) {
     using T = typename IO::elem_t;
     constexpr int NP = (3 * NROT + 1) / 2;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
@@ -412,10 +413,10 @@ __device__ __forceinline__ void ranges_image(const Img &im, int64_t pair, Ranges
     if (VEC) {
         const int ntiles = (int)(im.npix / (kThreads * G));
         if constexpr (SPLIT == 1)
-            pipe_for_each_group<IO>(pipe, base, im.plane_stride, ntiles, first_block, nblocks,
+            pipe_for_each_group<IO>(pipe, base, im.plane_stride, ntiles, first_block, nblocks, zero,
                                     [&](const typename IO::Raw &raw, int64_t) { group(raw); });
         else
-            pipe_for_each_group<IO, SPLIT>(pipe, base, im.plane_stride, ntiles, first_block, nblocks,
+            pipe_for_each_group<IO, SPLIT>(pipe, base, im.plane_stride, ntiles, first_block, nblocks, zero,
                                            [&](const typename IO::Raw &raw, int64_t, int) { group(raw); });
         p = (int64_t)ntiles * kThreads * G + threadIdx.x;   // the tail belongs to block 0
         step = kThreads;
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, NROT == 1 ? CT_RANGES_MINB1 : CT_RAN
     }
     __syncthreads();
     ranges_image<IO, VEC, (NROT > 2 ? NROT / 2 : NROT), (NROT > 2 ? 2 : 1)>(a.img[z], pair, sh, dec, n_rot, a.bound, pipe, blockIdx.x,
-                                                                            gridDim.x, a.stats != nullptr);
+                                                                            gridDim.x, a.stats != nullptr, a.zero);
     __syncthreads();
     if (threadIdx.x < 6 * n_rot) {
         const long long v = (&sh.key[0][0])[threadIdx.x];
@@ -658,6 +659,7 @@ struct HistArgs {
     unsigned int *tickets;
     int bins, copies_log2;
     int fuse_lut;
+    uint32_t zero;   // always 0 (ct_pipe.cuh: pipe_for_each_group)
     LutArgs lut;
 };
 
@@ -673,7 +675,7 @@ struct HistShared {
 template <typename IO, bool VEC, int CL2, typename Shared>  // CL2: log2(copies) when known at compile time, else -1
 __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Shared &sh,
                                            int bins, int copies_log2_rt, unsigned int *hist, HistPipe &pipe,
-                                           int first_block, int nblocks) {
+                                           int first_block, int nblocks, uint32_t zero) {
     const int copies_log2 = CL2 >= 0 ? CL2 : copies_log2_rt;
     using T = typename IO::elem_t;
     const T *base = reinterpret_cast<const T *>(im.data) + pair * im.image_stride;
@@ -705,7 +707,7 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Sh
     int64_t p = (int64_t)first_block * kThreads + threadIdx.x, step = (int64_t)nblocks * kThreads;
     if (VEC) {
         const int ntiles = (int)(im.npix / (kThreads * G));
-        pipe_for_each_group<IO>(pipe, base, im.plane_stride, ntiles, first_block, nblocks,
+        pipe_for_each_group<IO>(pipe, base, im.plane_stride, ntiles, first_block, nblocks, zero,
                                 [&](const typename IO::Raw &raw, int64_t) {
 #pragma unroll
                                     for (int q = 0; q < IO::NSUB; ++q) {
@@ -757,7 +759,7 @@ __global__ void __launch_bounds__(kThreads, 3) hist_kernel(HistArgs a) {
         __syncthreads();
         const int sel = a.kind[z] * 2 + a.vec[z];
 #define CT_HIST_CALL(T, L, V, CL2V) \
-    hist_image<PixelIO<T, L>, V, CL2V>(a.img[z], pair, sh, bins, a.copies_log2, hist, pipe, blockIdx.x, gridDim.x)
+    hist_image<PixelIO<T, L>, V, CL2V>(a.img[z], pair, sh, bins, a.copies_log2, hist, pipe, blockIdx.x, gridDim.x, a.zero)
 #define CT_CASE_3(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, 3); break;
 #define CT_CASE_g(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, -1); break;
         if (a.copies_log2 == 3) {  // bins <= 256: the default 255
@@ -823,6 +825,7 @@ struct RemapArgs {
     int32_t *status;
     int bins;
     int round_f32;
+    uint32_t zero;   // always 0 (ct_pipe.cuh: pipe_for_each_group)
 };
 enum { kDstState = 0, kDstF64 = 1, kDstU8 = 2, kDstF32 = 3, kDstU8Planar = 4 };
 
@@ -884,7 +887,7 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
     int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x, step = (int64_t)gridDim.x * kThreads;
     if (VEC) {
         const int ntiles = (int)(a.src.npix / (kThreads * G));
-        pipe_for_each_group<SIO>(pipe, src, a.src.plane_stride, ntiles, blockIdx.x, gridDim.x,
+        pipe_for_each_group<SIO>(pipe, src, a.src.plane_stride, ntiles, blockIdx.x, gridDim.x, a.zero,
                                  [&](const typename SIO::Raw &raw, int64_t tile0) {
 #pragma unroll
                                      for (int q = 0; q < SIO::NSUB; ++q) {

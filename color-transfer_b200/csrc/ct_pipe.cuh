@@ -145,9 +145,17 @@ __device__ __forceinline__ typename IO::Raw pipe_load_group(uint32_t src) {
 // SPLIT = 2: the two halves of the CTA do DIFFERENT work on the SAME pixels (K4 gives each half two of
 // the four rotations): every thread takes groups t % 128 and t % 128 + 128 of each tile and f is
 // called as f(raw, first_pixel_of_tile, u) for u = 0, 1.
+//
+// `zero` must be 0 and must come from a kernel argument (a value the compiler cannot know).  A warp
+// hands a stage back with an mbarrier arrive right after its shared-memory loads were ISSUED; the
+// arrive is not ordered behind those loads in hardware, so when the refill is fast (an L2-resident
+// image, an idle copy engine) the bulk copy of tile i + stages could land in the stage while a
+// quarter-warp wavefront of the load of tile i was still pending: a few pixels of tile i + stages
+// processed as tile i (seen as ~5 % wrong calls on 1080x860 float64 pairs).  The arrive's address is
+// therefore computed from the loaded registers (`& zero`), which makes it wait for the loads.
 template <typename IO, int SPLIT = 1, typename P, typename F>
 __device__ __forceinline__ void pipe_for_each_group(P &pipe, const typename IO::elem_t *img, int64_t plane,
-                                                    int ntiles, int first_tile, int tile_stride, F &&f) {
+                                                    int ntiles, int first_tile, int tile_stride, uint32_t zero, F &&f) {
     using T = typename IO::elem_t;
     constexpr int kStages = P::kNumStages;
     constexpr int G = IO::G;
@@ -179,8 +187,20 @@ __device__ __forceinline__ void pipe_for_each_group(P &pipe, const typename IO::
         typename IO::Raw raw[SPLIT];
 #pragma unroll
         for (int u = 0; u < SPLIT; ++u) raw[u] = pipe_load_group<IO>(pipe.stage + s * kTileBytes + my_off[u]);
+        uint32_t dep = 0;   // one word of every load instruction's result
+#pragma unroll
+        for (int u = 0; u < SPLIT; ++u) {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(raw[u].e);
+            if (IO::kU8) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) dep ^= w[k];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) dep ^= w[4 * k];
+            }
+        }
         __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(empty);  // this warp has copied its groups out
+        if ((threadIdx.x & 31) == 0) mbar_arrive(empty + (dep & zero));  // this warp has copied its groups out
         if (threadIdx.x == 0 && i + kStages < mine) {
             mbar_wait(empty, parity);  // all 8 warps are done with the stage
             issue(i + kStages, s);

@@ -12,14 +12,14 @@ import torch
 
 from . import _cabi
 
-_TORCH_DTYPE = {torch.float32: _cabi.CT_F32, torch.float64: _cabi.CT_F64}
+_TORCH_DTYPE = {torch.float32: _cabi.CT_F32, torch.float64: _cabi.CT_F64, torch.uint8: _cabi.CT_U8}
 
 
 def _check_images(x, name):
     if not x.is_cuda:
         raise ValueError(f"{name} must be a CUDA tensor (there is no CPU path)")
     if x.dtype not in _TORCH_DTYPE:
-        raise ValueError(f"{name} must be float32 or float64")
+        raise ValueError(f"{name} must be float32, float64 or uint8")
     if x.dim() == 3:
         x = x.unsqueeze(0)
     if x.dim() != 4 or x.shape[-1] != 3:
@@ -27,9 +27,9 @@ def _check_images(x, name):
     return x
 
 
-def batch_of(x):
+def batch_of(x, flags=0):
     """ct_batch for a [B,H,W,3] tensor that is either contiguous (HWC) or a permuted view of
-    contiguous [B,3,H,W] memory (CHW)."""
+    contiguous [B,3,H,W] memory (CHW).  ``flags``: _cabi.CT_BATCH_* bits."""
     b, h, w, _ = x.shape
     npix = h * w
     if x.is_contiguous():
@@ -39,7 +39,7 @@ def batch_of(x):
     else:
         keep = x.contiguous()
         layout = _cabi.CT_HWC
-    return _cabi.Batch(ctypes.c_void_p(keep.data_ptr()), npix, 3 * npix, 0, b, _TORCH_DTYPE[x.dtype], layout, 0), keep
+    return _cabi.Batch(ctypes.c_void_p(keep.data_ptr()), npix, 3 * npix, 0, b, _TORCH_DTYPE[x.dtype], layout, flags), keep
 
 
 def _handle_for(x, handle):
@@ -48,28 +48,53 @@ def _handle_for(x, handle):
     return h
 
 
-def linear_transfer(method, target, reference, out=None, handle=None):
+def _in_flags(x, as_float32):
+    return _cabi.CT_BATCH_U8_AS_F32 if (x.dtype == torch.uint8 and as_float32) else 0
+
+
+def _decoded_dtype(x, as_float32):
+    """The float dtype the reference would see for this image (a uint8 frame is what its loader decodes)."""
+    if x.dtype == torch.uint8:
+        return torch.float32 if as_float32 else torch.float64
+    return x.dtype
+
+
+def linear_transfer(method, target, reference, out=None, handle=None, as_float32=True, out_dtype=None, clamp=False):
     """method: _cabi.CT_REINHARD | CT_CCS | CT_MKL_*.  Returns a tensor shaped like target
-    (float64, or the target's dtype for Reinhard).  Asynchronous on the current stream."""
+    (float64, or the target's dtype for Reinhard).  Asynchronous on the current stream.
+
+    uint8 tensors are video frames / ``read_image`` tensors: they are decoded inside the kernels as
+    k/255 in float32 (``as_float32``, the reference's dataset loader, ref: utils/data.py:106) or float64
+    (``skimage.img_as_float``), and the result defaults to uint8 again (clip + round, img_as_ubyte).
+    ``out_dtype`` (torch.uint8 / float32 / float64) picks another result type, converted by the kernel
+    that writes it; ``clamp`` applies ``.clamp(0, 1)`` to a float32 result (ref: methods/__init__.py:30)."""
     t = _check_images(target, "target")
     r = _check_images(reference, "reference")
     h = _handle_for(t, handle)
-    out_dtype = t.dtype if method == _cabi.CT_REINHARD else torch.float64
+    if out_dtype is None:
+        if t.dtype == torch.uint8:
+            out_dtype = torch.uint8
+        else:
+            out_dtype = t.dtype if method == _cabi.CT_REINHARD else torch.float64
     if out is None:
         out = torch.empty(t.shape, dtype=out_dtype, device=t.device)
     o = _check_images(out, "out")
-    tb, k1 = batch_of(t)
-    rb, k2 = batch_of(r)
-    ob, k3 = batch_of(o)
+    tb, k1 = batch_of(t, _in_flags(t, as_float32))
+    rb, k2 = batch_of(r, _in_flags(r, as_float32))
+    ob, k3 = batch_of(o, _cabi.CT_BATCH_CLAMP01 if clamp else 0)
     if k3 is not o:
         raise ValueError("out must be contiguous")
     h.check(h.lib.ct_linear_transfer(h.h, method, tb, rb, ob, None, None))
     return out.view(target.shape) if target.dim() == 3 else out
 
 
-def idt_transfer(target, reference, rotations, bins=255, n_iter=4, out=None, workspace=None, handle=None):
+def idt_transfer(target, reference, rotations, bins=255, n_iter=4, out=None, workspace=None, handle=None,
+                 as_float32=True, out_dtype=None, clamp=False):
     """Fused IDT driver (2 + 2*n_iter launches).  rotations: float64 CUDA tensor
-    [B, n_iter, 3, 3].  Asynchronous on the current stream."""
+    [B, n_iter, 3, 3].  Asynchronous on the current stream.  The result is float64 (the reference's
+    dtype) for float images and uint8 for uint8 frames unless ``out`` / ``out_dtype`` say otherwise
+    (float32 and uint8 results are written by the last iteration's kernel, n_iter >= 2); see
+    ``linear_transfer`` for ``as_float32`` and ``clamp``."""
     t = _check_images(target, "target")
     r = _check_images(reference, "reference")
     h = _handle_for(t, handle)
@@ -78,13 +103,15 @@ def idt_transfer(target, reference, rotations, bins=255, n_iter=4, out=None, wor
     if rot.dtype != torch.float64 or not rot.is_cuda or not rot.is_contiguous():
         raise ValueError("rotations must be a contiguous float64 CUDA tensor [B, n_iter, 3, 3]")
     if out is None:
-        out = torch.empty(t.shape, dtype=torch.float64, device=t.device)
+        if out_dtype is None:
+            out_dtype = torch.uint8 if t.dtype == torch.uint8 else torch.float64
+        out = torch.empty(t.shape, dtype=out_dtype, device=t.device)
     o = _check_images(out, "out")
-    tb, k1 = batch_of(t)
-    rb, k2 = batch_of(r)
-    ob, k3 = batch_of(o)
-    if k3 is not o or o.dtype != torch.float64:
-        raise ValueError("out must be a contiguous float64 tensor")
+    tb, k1 = batch_of(t, _in_flags(t, as_float32))
+    rb, k2 = batch_of(r, _in_flags(r, as_float32))
+    ob, k3 = batch_of(o, _cabi.CT_BATCH_CLAMP01 if clamp else 0)
+    if k3 is not o:
+        raise ValueError("out must be a contiguous tensor")
     ws_ptr, ws_bytes = (None, 0)
     if workspace is not None:
         ws_ptr, ws_bytes = ctypes.c_void_p(workspace.data_ptr()), workspace.numel() * workspace.element_size()
@@ -108,9 +135,10 @@ class IdtStages:
     ``timer(name)`` may return a context manager to time individual launches.
     """
 
-    def __init__(self, target, reference, rotations, bins=255, n_iter=4, handle=None):
+    def __init__(self, target, reference, rotations, bins=255, n_iter=4, handle=None, as_float32=True):
         self.t = _check_images(target, "target")
         self.r = _check_images(reference, "reference")
+        self.as_float32 = as_float32
         self.h = _handle_for(self.t, handle)
         self.bins, self.n_iter = bins, n_iter
         b, hh, ww, _ = self.t.shape
@@ -124,8 +152,8 @@ class IdtStages:
         self.plane = (self.npix + 1) // 2 * 2
         self.state = torch.empty((b, 3, self.plane), dtype=torch.float64, device=dev) if n_iter >= 2 else None
         self.out = torch.empty(self.t.shape, dtype=torch.float64, device=dev)
-        self.tb, self._k1 = batch_of(self.t)
-        self.rb, self._k2 = batch_of(self.r)
+        self.tb, self._k1 = batch_of(self.t, _in_flags(self.t, as_float32))
+        self.rb, self._k2 = batch_of(self.r, _in_flags(self.r, as_float32))
         self.ob, _ = batch_of(self.out)
         if self.state is not None:
             self.sb = _cabi.Batch(ctypes.c_void_p(self.state.data_ptr()), self.npix, 3 * self.plane, self.plane, b,
@@ -175,7 +203,7 @@ class IdtStages:
         s = self._stage(it)
         last = it == self.n_iter - 1
         self.h.check(self.h.lib.ct_idt_remap(self.h.h, ctypes.byref(s), self.ob if last else self.sb,
-                                             1 if (it == 0 and self.t.dtype == torch.float32) else 0))
+                                             1 if (it == 0 and _decoded_dtype(self.t, self.as_float32) == torch.float32) else 0))
 
     def result(self):
         return self.out

@@ -116,15 +116,19 @@ def automated_color_grading(target, reference, *, rotations=None, out=None, hand
     return out
 
 
-def _idt_device_impl(target, reference, bins=255, n_iter=4):
-    """[B,H,W,3] CUDA tensors -> [B,H,W,3] float64 CUDA tensor.  Rotations are drawn pair by pair
-    from the global numpy RNG, n_iter per pair - the order a loop over the reference function sees."""
+def _idt_device_impl(target, reference, bins=255, n_iter=4, out_dtype=None, clamp=False):
+    """[B,H,W,3] CUDA tensors (float, or uint8 frames decoded as float32) -> [B,H,W,3] CUDA tensor
+    (float64 unless ``out_dtype`` says otherwise).  Rotations are drawn pair by pair from the global
+    numpy RNG, n_iter per pair - the order a loop over the reference function sees."""
     import torch
 
     from .. import device
     b = target.shape[0]
     rot = np.stack([draw_rotations(n_iter) for _ in range(b)])
-    return device.idt_transfer(target, reference, torch.from_numpy(rot).to(target.device), bins, n_iter)
+    if out_dtype is None:
+        out_dtype = torch.float64
+    return device.idt_transfer(target, reference, torch.from_numpy(rot).to(target.device), bins, n_iter,
+                               out_dtype=out_dtype, clamp=clamp)
 
 
 iterative_distribution_transfer.device_impl = _idt_device_impl

@@ -26,6 +26,26 @@ def _as_image(x, name):
     return a
 
 
+def _img_as_float(x, name):
+    """What ``skimage.color.rgb2lab`` does to its argument first (``img_as_float`` via
+    ``_prepare_colorarray``, ref: methods/linear.py:25-26): unsigned integers are divided by their
+    maximum, float16 becomes float32, float32 / float64 are kept."""
+    a = np.asarray(x)
+    if a.ndim != 3 or a.shape[-1] != 3:
+        raise ValueError(f"{name} must have shape [H, W, 3], got {a.shape}")
+    if a.dtype == np.float32 or a.dtype == np.float64:
+        return a
+    if a.dtype == np.float16:
+        return a.astype(np.float32)
+    if a.dtype.kind == "u":
+        return a.astype(np.float64) / np.iinfo(a.dtype).max
+    if a.dtype.kind == "i":   # signed integers map to [-1, 1]
+        return a.astype(np.float64) / np.iinfo(a.dtype).max
+    if a.dtype == np.bool_:
+        return a.astype(np.float64)
+    return a.astype(np.float64)
+
+
 def _run(method, target, reference, out_dtype, out=None, handle=None):
     t = _as_image(target, "target")
     r = _as_image(reference, "reference")
@@ -38,6 +58,9 @@ def _run(method, target, reference, out_dtype, out=None, handle=None):
         raise ValueError("out must be a C-contiguous array of the target's shape and the result dtype")
     ob, _ = _cabi.batch_from_numpy(out)
     rc = h.lib.ct_linear_transfer_host(h.h, method, tb, rb, ob)
+    if rc == _cabi.CT_E_SINGULAR and method == _cabi.CT_CCS:
+        # 1 / sqrt(0) in the reference (linear.py:73-78): inf / NaN propagate, nothing is raised
+        rc = _cabi.CT_OK
     if rc in (_cabi.CT_E_NOT_PD, _cabi.CT_E_SINGULAR):
         # np.linalg.cholesky / np.linalg.inv raise LinAlgError on such covariances
         raise np.linalg.LinAlgError(h.lib.ct_last_error(h.h).decode())
@@ -52,9 +75,13 @@ def color_transfer_between_images(target, reference, *, out=None, handle=None):
     Per-channel mean / standard-deviation matching in CIE-Lab.  Returns RGB clipped to [0, 1]
     with the float dtype of ``target`` (float32 stays float32 as in scikit-image >= 0.19).
     """
-    t = np.asarray(target)
-    out_dtype = np.float32 if t.dtype == np.float32 else np.float64
-    return _run(_cabi.CT_REINHARD, target, reference, out_dtype, out, handle)
+    t = _img_as_float(target, "target")
+    r = _img_as_float(reference, "reference")
+    # (target_lab - mean_t) * std_r / std_t + mean_r promotes to the wider of the two float dtypes
+    out_dtype = np.result_type(t.dtype, r.dtype)
+    if t.dtype != out_dtype:
+        t = t.astype(out_dtype)
+    return _run(_cabi.CT_REINHARD, t, r, out_dtype, out, handle)
 
 
 def color_transfer_in_correlated_color_space(target, reference, *, out=None, handle=None):
@@ -78,10 +105,11 @@ def monge_kantorovitch_color_transfer(target, reference, decomposition="MK", *, 
 
 
 def _device_impl(method):
-    def run(target, reference):
-        """[B,H,W,3] CUDA tensors -> [B,H,W,3] CUDA tensor; same kernels, no host round trip."""
+    def run(target, reference, out_dtype=None, clamp=False):
+        """[B,H,W,3] CUDA tensors (float, or uint8 frames decoded as float32 like the reference's dataset
+        loader) -> [B,H,W,3] CUDA tensor; same kernels, no host round trip."""
         from .. import device
-        return device.linear_transfer(method, target, reference)
+        return device.linear_transfer(method, target, reference, out_dtype=out_dtype, clamp=clamp)
     return run
 
 

@@ -325,7 +325,20 @@ def test_pair0964_notebook_and_cli_variants(api, pair0964):
     np.random.seed(42)
     out = it.iterative_distribution_transfer(target, right)
     np.random.seed(42)
-    assert _close(out, oracle.iterative_distribution_transfer(target, right))[0] < 1e-9
+    want, traces = oracle.idt_instrumented(target, right, keep_arrays=False)
+    if np.max(np.abs(out - want)) >= 1e-9:   # say which stage went wrong before failing
+        np.random.seed(42)
+        tr = {}
+        again = it.iterative_distribution_transfer(target, right, trace=tr)
+        report = [f"first call err {np.max(np.abs(out - want)):.3e}, repeated call err {np.max(np.abs(again - want)):.3e}"]
+        for i in range(4):
+            report.append(f"it {i}: lo {np.max(np.abs(tr['lo'][i] - traces[i]['lo'])):.2e} hi {np.max(np.abs(tr['hi'][i] - traces[i]['hi'])):.2e} "
+                          f"counts_t {int(np.abs(tr['counts_t'][i] - traces[i]['counts_t']).sum())} "
+                          f"counts_r {int(np.abs(tr['counts_r'][i] - traces[i]['counts_r']).sum())}")
+        bad = np.argwhere(np.abs(out - want).max(axis=2) >= 1e-9)
+        report.append(f"{len(bad)} bad pixels, rows {bad[:, 0].min()}..{bad[:, 0].max()}, cols {bad[:, 1].min()}..{bad[:, 1].max()}")
+        pytest.fail("; ".join(report))
+    assert _close(out, want)[0] < 1e-9
     # 1c: float32, CHW memory viewed HWC (ref: methods/__init__.py:21-22)
     t32 = np.ascontiguousarray(target.astype(np.float32).transpose(2, 0, 1)).transpose(1, 2, 0)
     r32 = np.ascontiguousarray(right.astype(np.float32).transpose(2, 0, 1)).transpose(1, 2, 0)
