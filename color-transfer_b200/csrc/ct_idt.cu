@@ -817,6 +817,7 @@ struct RemapArgs {
     int dst_kind;    // kDstState (planar fp64 state), kDstF64 (final fp64 HWC), or a fused final conversion:
                      // kDstU8 / kDstU8Planar (clip + round to uint8), kDstF32 (float32 HWC, optional clamp)
     int clamp;
+    int dst_vec;     // the destination allows vector stores (else element stores; the source still streams through TMA)
     const double *rot, *rot_next;
     int64_t rot_stride;
     int64_t *keys_next;
@@ -847,7 +848,7 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
     TD *dst = reinterpret_cast<TD *>(a.dst.data) + pair * a.dst.image_stride;
     constexpr int G = SIO::G, GS = SIO::GS;
     const Decode dec{sh.dec_d, sh.dec_f};
-    const bool clamp = a.clamp != 0;
+    const bool clamp = a.clamp != 0, dst_vec = a.dst_vec != 0;
     const int bins = a.bins;
     const int E = CT_IDT_EDGE_STRIDE(bins);
     double r[9], rn[9], lo[3], inv[3];
@@ -895,7 +896,8 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
                                          SIO::unpack_sub(raw, q, dec, x);
 #pragma unroll
                                          for (int i = 0; i < GS; ++i) one(x[i], y[i]);
-                                         DIO::template store<true, GS>(dst, a.dst.plane_stride, pipe_sub_pixel0<SIO>(tile0, q), y, clamp);
+                                         if (dst_vec) DIO::template store<true, GS>(dst, a.dst.plane_stride, pipe_sub_pixel0<SIO>(tile0, q), y, clamp);
+                                         else DIO::template store<false, GS>(dst, a.dst.plane_stride, pipe_sub_pixel0<SIO>(tile0, q), y, clamp);
                                      }
                                  });
         p = (int64_t)ntiles * kThreads * G + threadIdx.x;   // the tail belongs to block 0
@@ -918,7 +920,7 @@ __device__ __forceinline__ void remap_dispatch(const RemapArgs &a, int64_t pair,
                                                const double *tab, RemapPipe &pipe, bool next, double (&mn)[6], bool &bad) {
     using StateIO = PixelIO<double, CT_CHW>;
     using FinalIO = PixelIO<double, CT_HWC>;
-    constexpr bool kFromState = same_io<SIO, StateIO>::value && VEC;
+    constexpr bool kFromState = same_io<SIO, StateIO>::value;
     if (kFromState && a.dst_kind >= kDstU8) {
         if (a.dst_kind == kDstU8) remap_image<SIO, PixelIO<uint8_t, CT_HWC>, VEC, false, false>(a, pair, sh, tab, pipe, mn, bad);
         else if (a.dst_kind == kDstU8Planar) remap_image<SIO, PixelIO<uint8_t, CT_CHW>, VEC, false, false>(a, pair, sh, tab, pipe, mn, bad);
@@ -1198,14 +1200,15 @@ int launch_remap(ct_context *h, const ct_idt_stage *s, const ct_batch *dst, int 
     a.src = img_of(s->target);
     a.dst = imgout_of(dst);
     a.kind = src_kind(s->target);
-    a.vec = vec_ok(s->target) && vec_ok(dst);
+    a.vec = vec_ok(s->target);
+    a.dst_vec = vec_ok(dst);
     a.u8_as_f32 = (s->target->flags & CT_BATCH_U8_AS_F32) != 0;
     a.clamp = (dst->flags & CT_BATCH_CLAMP01) != 0;
     if (dst->dtype == CT_F64) {
         a.dst_kind = dst->layout == CT_CHW ? kDstState : kDstF64;
     } else {
         // fused final conversion: only from the planar fp64 state (the last of n_iter >= 2 iterations)
-        const bool from_state = s->target->dtype == CT_F64 && s->target->layout == CT_CHW && a.vec;
+        const bool from_state = s->target->dtype == CT_F64 && s->target->layout == CT_CHW;
         if (!from_state) return fail(h, CT_E_UNSUPPORTED, "uint8 / float32 IDT output needs the planar float64 state as the source");
         if (dst->dtype == CT_U8) a.dst_kind = dst->layout == CT_HWC ? kDstU8 : kDstU8Planar;
         else if (dst->dtype == CT_F32 && dst->layout == CT_HWC) a.dst_kind = kDstF32;

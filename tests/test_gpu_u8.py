@@ -58,10 +58,11 @@ def test_linear_u8_equals_decoded_float_path(mods, b, h, w, as_float32, planar):
         assert got.dtype == torch.uint8 and got.shape == (b, h, w, 3)
         ref = device.linear_transfer(code, torch.from_numpy(tf).cuda(), torch.from_numpy(rf).cuda())
         assert np.array_equal(got.cpu().numpy(), _quantise(ref.cpu().numpy())), f"method {code}"
-        # float results straight from uint8 frames: what the float path computes (the statistics are summed
-        # in another thread order - 16 instead of 4 pixels per thread - hence a last-ulp tolerance)
+        # float results straight from uint8 frames: what the float path computes.  The statistics are summed
+        # in another thread order (16 instead of 4 or 2 pixels per thread): last-ulp differences, and for
+        # Reinhard the fp32 group sums of the Lab statistics pass differ at 1e-8.
         f = device.linear_transfer(code, dev8(t8), dev8(r8), as_float32=as_float32, out_dtype=ref.dtype)
-        tol = 2e-6 if ref.dtype == torch.float32 else 1e-12
+        tol = 2e-6 if (ref.dtype == torch.float32 or code == _cabi.CT_REINHARD) else 1e-12
         assert float((f.double() - ref.double()).abs().max()) <= tol
 
 
@@ -139,7 +140,9 @@ def test_runner_uint8_tensors(mods):
     t8, r8 = _frames(3, 40, 56, 1300)
     u8 = {"target": torch.from_numpy(np.ascontiguousarray(t8.transpose(0, 3, 1, 2))).cuda(),
           "reference": torch.from_numpy(np.ascontiguousarray(r8.transpose(0, 3, 1, 2))).cuda()}
-    fl = {k: v.float() / 255 for k, v in u8.items()}
+    # the reference divides on the CPU (correctly rounded); torch's CUDA `/ 255` multiplies by 1/255
+    fl = {"target": torch.from_numpy(np.ascontiguousarray((t8 / np.float32(255)).astype(np.float32).transpose(0, 3, 1, 2))).cuda(),
+          "reference": torch.from_numpy(np.ascontiguousarray((r8 / np.float32(255)).astype(np.float32).transpose(0, 3, 1, 2))).cuda()}
     for spec in ("methods.linear.color_transfer_between_images", "methods.linear.monge_kantorovitch_color_transfer",
                  "methods.iterative.iterative_distribution_transfer"):
         runner = methods.Runner(spec)
@@ -148,12 +151,14 @@ def test_runner_uint8_tensors(mods):
         np.random.seed(3)
         b = runner(fl)
         assert a.dtype == torch.float32 and a.shape == (3, 3, 40, 56)
-        assert torch.equal(a, b), spec
+        exact = "iterative" in spec      # IDT has no floating-point reduction; the linear statistics are summed
+        tol = 0.0 if exact else 1e-6     # in another thread order for uint8 groups (last-ulp differences)
+        assert float((a - b).abs().max()) <= tol, spec
         np.random.seed(3)
         runner._clamp_fused = True
         c = runner(u8)
         runner._clamp_fused = False
-        assert torch.equal(c, b.clamp(0, 1)), spec
+        assert float((c - b.clamp(0, 1)).abs().max()) <= tol, spec
 
 
 def test_reinhard_numpy_wrapper_integer_inputs(mods):
