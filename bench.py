@@ -5,20 +5,30 @@
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (config.workload): BASELINE.json configs[3] - synthetic 4K VR180 stereo video,
-3840x2160 per eye, float32 HWC frames (the reference CLI dtype), iterative distribution
-transfer with bins=255, n_iter=4, rotations pre-drawn per frame after np.random.seed(42),
-frames sharded frame-parallel over the ranks with no data-path collective (weak scaling:
-every rank processes --frames frames per step).  A "step" is one pass of IDT over one batch
-of frames.
+3840x2160 per eye, iterative distribution transfer with bins=255, n_iter=4, rotations pre-drawn
+per frame after np.random.seed(42), frames sharded frame-parallel over the ranks with no
+data-path collective (weak scaling: every rank processes the same number of frames per step).
+A "step" is `--passes` passes of IDT over the rank's `--frames` resident frame pairs
+(8 x 12 = 96 frame pairs per rank and step by default, ~55 ms, so that K = 20 steps time > 1 s).
 
-value      device-resident: frames already in HBM, CUDA-event time on the launching stream.
-e2e        the batched host API (color_transfer_b200.batch.idt_frames -> ct_idt_transfer_host):
-           pinned host frames in, pinned float64 result out, copies inside the timed region.
-roofline   the dominant kernel (largest share of the step), algorithmic bytes / its CUDA-event
-           time, against MEASURED_PEAKS.json hbm_gbs.
-cpu_baseline  the numpy oracle port (the reference's own numpy calls) on host cores, bounded
-           sample, rank 0 at N=1 only.
---impl reference  the same oracle port with a process pool over frames on all usable cores.
+value      device-resident float32 frames (the reference CLI dtype), CUDA-event time on the launching
+           stream, max over ranks.
+e2e        the headline: the video API (color_transfer_b200.batch.idt_frames_u8 ->
+           ct_idt_transfer_host_u8): pinned uint8 frames in, pinned uint8 frames out, the kernels
+           decode / encode as they read / write, copies inside the timed region.
+e2e_float  the same through the float API (float32 frames in, the reference's float64 result out).
+host_dma   what the box's host<->device DMA gives ALL ranks together (pure pinned copies, both
+           directions at once): the ceiling of any end-to-end number at N GPUs.
+roofline   the dominant kernel (largest share of the step): algorithmic bytes / its CUDA-event time
+           (per-launch events inside the fused driver, ct_profile_*), against MEASURED_PEAKS.json.
+linear     configs[2]: 1035 pairs of 960x540 float32, Reinhard / MKL / CCS, frame-parallel, both
+           distributions, per-rank device-resident batches (weak scaling like the main metric).
+rowshard   (N > 1) configs[4]: one 16384x16384 float32 pair, rows sharded over the ranks with NCCL
+           all-reduces of range keys / counts / moments, plus a parity check of the sharded result
+           against the unsharded one on a 4096x4096 pair of the same generator.
+cpu_baseline  the numpy oracle port on ONE host core, bounded sample, rank 0 at N=1 only.
+--impl reference  the same oracle port with a process pool over frames on all usable cores, on the
+           same 4K uint8 frames (decode -> IDT -> encode).
 """
 
 import argparse
@@ -37,6 +47,8 @@ BINS, N_ITER = 255, 4
 METRIC = "stereopair Mpix/s (IDT, 4K stereo video, frame-parallel)"
 # algorithmic bytes per target pixel, IDT, float32 frames, n_iter=4 (SURVEY.md 8d / BASELINE.md 4)
 IDT_BYTES_PER_PIXEL_F32 = 24 + (24 + 36) + 3 * (36 + 48)
+# ... uint8 frames in and out (3 B/px images, fp64 state): ranges 6, hist 6 + 3*27, remap 27 + 2*48 + 27
+IDT_BYTES_PER_PIXEL_U8 = 6 + (6 + 3 * 27) + (27 + 2 * 48 + 27)
 
 
 # The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's "NCCL version ..."
@@ -62,36 +74,39 @@ def _claim_stdout():
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=8, help="frame pairs per rank per step")
-    ap.add_argument("--e2e-frames", type=int, default=8)
+    ap.add_argument("--frames", type=int, default=8, help="resident frame pairs per rank")
+    ap.add_argument("--passes", type=int, default=12, help="passes over the resident frames per step")
+    ap.add_argument("--e2e-frames", type=int, default=32, help="frame pairs per end-to-end step (one API call)")
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--width", type=int, default=W4K)
     ap.add_argument("--stress", action="store_true", help="i.i.d. uniform frames instead of the smooth field")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the linear / rowshard / single-pair sections")
     ap.add_argument("--kernels-only", action="store_true", help="profiling aid: only the timed device steps")
-    ap.add_argument("--linear-only", action="store_true", help="profiling aid: only the linear-transfer extras")
-    ap.add_argument("--workload", default="video4k", choices=["video4k", "rowshard"],
-                    help="video4k: configs[3] (default, the bench line); rowshard: configs[4], one 16384x16384 pair "
-                         "split by rows over the ranks with NCCL all-reduces of range keys / counts / moments")
-    ap.add_argument("--side", type=int, default=16384, help="rowshard: side of the square pair")
+    ap.add_argument("--linear-only", action="store_true", help="profiling aid: only the linear section")
+    ap.add_argument("--linear-pairs", type=int, default=1035)
+    ap.add_argument("--rowshard-side", type=int, default=16384, help="side of the square row-sharded pair")
+    ap.add_argument("--ref-workers", type=int, default=0, help="reference arm: processes (0 = all usable cores)")
     return ap.parse_args()
 
 
 def ncu_traffic_bytes_per_pixel(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per target pixel of `kernel`, from the committed
-    `ncu --set full` capture of this same command (profiles/r01_traffic.json, written by
+    `ncu --set full` capture of this same command (profiles/r02_traffic.json, else r01; written by
     tools/ncu_report.py); None if there is no capture for it."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f)["dram_bytes_per_pixel"]
-        vals = [v for k, vs in t.items() if k.startswith(kernel) for v in vs]
-        return sum(vals) / len(vals) if vals else None
-    except Exception:  # noqa: BLE001
-        return None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)["dram_bytes_per_pixel"]
+            vals = [v for k, vs in t.items() if k.startswith(kernel) for v in vs]
+            if vals:
+                return sum(vals) / len(vals), "profiles/" + name
+        except Exception:  # noqa: BLE001
+            continue
+    return None, None
 
 
 def measured_peaks():
@@ -155,7 +170,8 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ CPU arm
 def _cpu_frame(args):
-    """One oracle IDT on one synthetic frame pair; runs in a worker process."""
+    """One frame pair of the video path on the CPU: uint8 frames -> k/255 float32 (the reference loader,
+    utils/data.py:106) -> oracle IDT -> clip + round to uint8 (img_as_ubyte).  Runs in a worker process."""
     seed, h, w, rotations, blas_threads = args
     import numpy as np
     if blas_threads:
@@ -164,11 +180,14 @@ def _cpu_frame(args):
             threadpool_limits(blas_threads)
         except Exception:  # noqa: BLE001
             pass
-    from color_transfer_b200_synth import frame_pair  # registered by _register_synth()
+    from color_transfer_b200_synth import frame_pair_u8  # registered by _register_synth()
     from oracle import reference_numpy as oracle
-    t, r = frame_pair(h, w, seed, np.float32)
+    t8, r8 = frame_pair_u8(h, w, seed)
     t0 = time.perf_counter()
-    oracle.iterative_distribution_transfer(t, r, BINS, N_ITER, rotations=rotations)
+    t = t8 / np.float32(255)
+    r = r8 / np.float32(255)
+    out = oracle.iterative_distribution_transfer(t, r, BINS, N_ITER, rotations=rotations)
+    np.rint(np.clip(out, 0, 1) * 255).astype(np.uint8)
     return time.perf_counter() - t0
 
 
@@ -188,63 +207,76 @@ def usable_workers(bytes_per_worker):
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
         import psutil
-        n = min(n, max(1, int(psutil.virtual_memory().available * 0.5 // bytes_per_worker)))
+        n = min(n, max(1, int(psutil.virtual_memory().available * 0.6 // bytes_per_worker)))
     except Exception:  # noqa: BLE001
         pass
-    return max(1, min(n, 64))
+    return max(1, min(n, 128))
 
 
-def cpu_oracle_throughput(h, w, workers, waves, first_seed=2000):
-    """Mpix/s of the oracle port: `workers` frames in flight, `waves` rounds."""
-    import multiprocessing as mp
+class CpuPool:
+    """A pool of worker processes that stays up for the whole reference run (steps time only the frames)."""
 
+    def __init__(self, workers):
+        import multiprocessing as mp
+        _register_synth()
+        self.workers = workers
+        self.pool = mp.get_context("fork").Pool(workers) if workers > 1 else None
+
+    def step(self, h, w, first_seed, rotations):
+        """One frame pair per worker, all in flight together; returns (Mpix/s, wall seconds of the step)."""
+        jobs = [(first_seed + k, h, w, rotations[k], 1 if self.workers > 1 else 0) for k in range(self.workers)]
+        t0 = time.perf_counter()
+        if self.pool is None:
+            busy = [_cpu_frame(j) for j in jobs]
+            wall = sum(busy)          # exclude the synthetic-frame generation
+        else:
+            busy = self.pool.map(_cpu_frame, jobs, chunksize=1)
+            wall = max(busy)          # frames run concurrently: the step lasts as long as its slowest frame
+        total = time.perf_counter() - t0
+        return self.workers * h * w / 1e6 / wall, wall, total
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+
+def draw_rotations_np(n_frames):
     import numpy as np
     import scipy.stats
-    _register_synth()
-    np.random.seed(42)
-    jobs = []
-    for k in range(workers * waves):
-        rot = np.stack([scipy.stats.special_ortho_group.rvs(3) for _ in range(N_ITER)])
-        jobs.append((first_seed + k, h, w, rot, 1 if workers > 1 else 0))
-    t0 = time.perf_counter()
-    if workers == 1:
-        busy = [_cpu_frame(j) for j in jobs]
-        wall = sum(busy)          # exclude the synthetic-frame generation
-    else:
-        ctx = mp.get_context("fork")
-        with ctx.Pool(workers) as pool:
-            busy = pool.map(_cpu_frame, jobs, chunksize=1)
-        # frames run concurrently: the wall time of the transfer part is the slowest lane
-        lanes = [sum(busy[i::workers]) for i in range(workers)]
-        wall = max(lanes)
-    total_wall = time.perf_counter() - t0
-    mpix = len(jobs) * h * w / 1e6
-    return mpix / wall, wall, total_wall
+    return [np.stack([scipy.stats.special_ortho_group.rvs(3) for _ in range(N_ITER)]) for _ in range(n_frames)]
 
 
 def run_reference_arm(a):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """The reference's own CPU path (the numpy oracle port of methods/iterative.py; the reference itself is
+    not importable on the box) on the SAME workload: 3840x2160 uint8 frame pairs, bins / n_iter / rotations
+    as in our arm.  A step is a bounded sample of it: one frame pair per host core, all in flight."""
+    import numpy as np
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    # bounded sample: quarter-area crops of the 4K frames (IDT cost is linear in pixels)
-    h, w = a.height // 2, a.width // 2
-    workers = usable_workers(bytes_per_worker=h * w * 3 * 8 * 14)
-    values = []
-    for _ in range(a.warmup if a.warmup < 2 else 1):
-        cpu_oracle_throughput(h, w, workers, 1)
-    t_steps = []
-    for s in range(a.steps):
-        v, wall, _ = cpu_oracle_throughput(h, w, workers, 1, first_seed=2000 + s * workers)
-        values.append(v)
-        t_steps.append(wall)
+    h, w = a.height, a.width
+    workers = a.ref_workers or usable_workers(bytes_per_worker=h * w * 3 * 8 * 16)
+    pool = CpuPool(workers)
+    np.random.seed(42)
+    warm = max(a.warmup, 0)
+    values, walls = [], []
+    for s in range(warm + a.steps):
+        rot = draw_rotations_np(workers)
+        v, wall, _ = pool.step(h, w, 2000 + s * workers, rot)
+        if s >= warm:
+            values.append(v)
+            walls.append(wall)
+    pool.close()
     value = sum(values) / len(values)
-    sample = (f"{workers} frames in flight per step (one per process), each a {w}x{h} quarter-area frame of the "
-              f"4K workload, float32 in, bins={BINS}, n_iter={N_ITER}; numpy oracle port of methods/iterative.py")
+    sample = (f"each step = {workers} frame pairs of the workload ({w}x{h} uint8 per eye) in flight together, one per process "
+              f"(BLAS pinned to 1 thread per process): decode k/255 float32 -> numpy oracle port of methods/iterative.py "
+              f"(bins={BINS}, n_iter={N_ITER}) -> clip + round to uint8")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * sum(t_steps) / len(t_steps),
+        "steps": a.steps, "warmup": warm, "ms_per_step": 1e3 * sum(walls) / len(walls),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(a, frames=workers),
+        "config": workload_config(a),
+        "frame_pairs_per_step": workers,
         "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -252,12 +284,14 @@ def run_reference_arm(a):
     emit(line)
 
 
-def workload_config(a, frames):
+def workload_config(a):
+    """Identical for both arms (how many frames a step holds is reported beside it, not inside)."""
     return {"workload": "configs[3]: synthetic 4K VR180 stereo video, IDT frame-parallel",
-            "frame": [a.height, a.width, 3], "frames_per_rank_per_step": frames, "input_dtype": "float32",
-            "bins": BINS, "n_iter": N_ITER, "distribution": "uniform-noise" if a.stress else "smooth-field+noise",
+            "frame": [a.height, a.width, 3], "bins": BINS, "n_iter": N_ITER,
+            "distribution": "uniform-noise" if a.stress else "smooth-field+noise",
+            "frames": "uint8 video frames decoded as k/255 float32 (utils/data.py:106); float32 frames for the device-resident value",
             "parallelism": f"frame-parallel x{a.gpus}, no collective",
-            "l2": "working set per frame (99.5 MB/eye in, 199 MB state) exceeds the 126 MB L2"}
+            "l2": "working set per frame pair (200 MB float32 in, 199 MB state) exceeds the 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -285,8 +319,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     handle = _cabi.default_handle(local)
-    H, W, F = a.height, a.width, a.frames
+    H, W, F, P = a.height, a.width, a.frames, max(1, a.passes)
     npix = H * W
+    warmup = max(a.warmup, 3)
 
     def barrier():
         if world > 1:
@@ -300,13 +335,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    ctx = dict(torch=torch, dist=dist, device=device, synth=synth, _cabi=_cabi, batch=batch, handle=handle, dev=dev,
+               world=world, rank=rank, barrier=barrier, max_over_ranks=max_over_ranks, peak=measured_peaks()[0])
+
     if a.linear_only:
-        emit(linear_extras(torch, device, synth, _cabi, handle, dev, measured_peaks()[0]))
-        return
-    if a.workload == "rowshard":
-        run_rowshard(a, torch, dist, device, synth, _cabi, handle, dev, world, rank, barrier, max_over_ranks)
-        if world > 1:
-            dist.destroy_process_group()
+        line = linear_section(a, ctx)
+        if rank == 0:
+            emit(line)
         return
 
     # frames k = rank, rank + world, ...: rotations pre-drawn in frame order after seed 42
@@ -317,10 +352,14 @@ def main():
     out = torch.empty((F, H, W, 3), dtype=torch.float64, device=dev)
     ws = device.idt_workspace(npix, F, BINS, N_ITER, dev)
 
-    def step():
+    def one_pass():
         device.idt_transfer(tgt, ref, my_rot, BINS, N_ITER, out=out, workspace=ws, handle=handle)
 
-    for _ in range(max(a.warmup, 3)):
+    def step():
+        for _ in range(P):
+            one_pass()
+
+    for _ in range(warmup):
         step()
     sampler = ClockSampler(local)
     barrier()
@@ -336,92 +375,62 @@ def main():
     launches = handle.launches - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / a.steps
-    value = world * F * npix / 1e6 / (ms_step / 1e3)
+    value = world * F * P * npix / 1e6 / (ms_step / 1e3)
     if a.kernels_only:
         if rank == 0:
-            emit({"metric": METRIC, "value": value, "unit": "Mpix/s", "ms_per_step": ms_step,
+            emit({"metric": METRIC, "value": value, "unit": "Mpix/s", "ms_per_step": ms_step, "ms_per_pass": ms_step / P,
                   "gpu_launches": int(launches), "note": "kernels-only profiling run"})
         return
 
-    # ---- per-kernel breakdown with CUDA events (stage API == the same kernels, unfused LUT off)
-    stages = device.IdtStages(tgt, ref, my_rot, BINS, N_ITER, handle=handle)
-    times = {}
-
-    class Timer:
-        def __init__(self, name):
-            self.name = name
-
-        def __enter__(self):
-            self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            self.a.record()
-
-        def __exit__(self, *exc):
-            self.b.record()
-            self.b.synchronize()
-            times.setdefault(self.name, []).append(self.a.elapsed_time(self.b))
-
-    stages.run(timer=Timer)
-    times.clear()
-    for _ in range(3):
-        stages.run(timer=Timer)
-    del stages
-    kern = {}
-    for name, v in times.items():
+    # ---- per-kernel times: CUDA events after every launch of the fused driver, on two extra steps of the
+    # very loop timed above (ct_profile_*); reported per pass over the F resident frame pairs
+    handle.profile(True)
+    step()
+    step()
+    prof = handle.profile_read(16384)
+    handle.profile(False)
+    n_pass = 2 * P
+    kern_ms, kern_launches = {}, {}
+    for name, ms in prof:
         kind = name.split("_")[0]
-        kern.setdefault(kind, []).append((name, sum(v) / len(v)))
-    share = {k: sum(t for _, t in v) for k, v in kern.items()}
-    dominant = max(share, key=share.get)
-    # algorithmic bytes per pixel of each launch of the dominant kernel (float32 frames, fp64 state)
-    per_launch_bytes = {"hist": lambda it: (12 if it == 0 else 24) + 12, "remap": lambda it: (12 if it == 0 else 24) + 24,
-                        "ranges": lambda it: 12}
-    achieved = []
-    for name, ms in kern[dominant]:
-        it = int(name.split("_")[1]) if name.split("_")[1].isdigit() else 0
-        achieved.append(per_launch_bytes[dominant](it) * npix * F / (ms / 1e3) / 1e9)
+        kern_ms[kind] = kern_ms.get(kind, 0.0) + ms / n_pass
+        kern_launches[kind] = kern_launches.get(kind, 0) + 1
+    # algorithmic bytes per pixel and pass of each kernel kind (float32 frames, fp64 state)
+    kind_bytes = {"hist": (12 + 12) + 3 * (24 + 12), "remap": (12 + 24) + 3 * (24 + 24), "ranges": 12 + 12, "seed": 0}
+    dominant = max((k for k in kern_ms if k in ("hist", "remap", "ranges")), key=lambda k: kern_ms[k])
     peak, peak_kind = measured_peaks()
-    ach = sum(achieved) / len(achieved)
+    launches_per_pass = kern_launches[dominant] / n_pass
+    alg_bytes_launch = kind_bytes[dominant] * npix * F / launches_per_pass
+    avg_launch_ms = kern_ms[dominant] / launches_per_pass
+    ach = alg_bytes_launch / (avg_launch_ms / 1e3) / 1e9
     kname = {"hist": "hist_kernel", "remap": "remap_kernel", "ranges": "ranges_kernel"}[dominant]
-    bpp = ncu_traffic_bytes_per_pixel(kname)
-    alg_bytes = sum(per_launch_bytes[dominant](int(n.split("_")[1]) if n.split("_")[1].isdigit() else 0) for n, _ in kern[dominant]) \
-        * npix * F / len(kern[dominant])
+    bpp, bpp_src = ncu_traffic_bytes_per_pixel(kname)
+    step_gbps = IDT_BYTES_PER_PIXEL_F32 * npix * F * P / (ms_step / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": ach, "peak": peak, "peak_source": peak_kind, "unit": "GB/s", "frac": ach / peak,
-                "algorithmic_bytes_per_launch": alg_bytes,
+                "algorithmic_bytes_per_launch": alg_bytes_launch, "avg_launch_ms": avg_launch_ms,
+                "launches_per_pass": launches_per_pass,
                 "traffic": None if bpp is None else bpp * npix * F,
-                "traffic_source": None if bpp is None else "profiles/r01_traffic.json: ncu dram bytes per pixel of the steady-state launches x pixels per launch",
-                "kernel_ms": {k: round(sum(t for _, t in v), 4) for k, v in kern.items()},
-                "step_algorithmic_GBps": IDT_BYTES_PER_PIXEL_F32 * npix * F / (ms_step / 1e3) / 1e9,
-                "step_frac": IDT_BYTES_PER_PIXEL_F32 * npix * F / (ms_step / 1e3) / 1e9 / peak}
+                "traffic_source": None if bpp is None else bpp_src + ": ncu dram bytes per pixel of the steady-state launches x pixels per launch",
+                "kernel_ms_per_pass": {k: round(v, 4) for k, v in kern_ms.items()},
+                "kernel_frac": {k: round(kind_bytes[k] * npix * F / (v / 1e3) / 1e9 / peak, 4) for k, v in kern_ms.items() if kind_bytes.get(k)},
+                "timing": "CUDA events after every launch of the fused driver (ct_profile_*), two steps right after the timed region",
+                "step_algorithmic_GBps": step_gbps, "step_frac": step_gbps / peak}
+    del ws
 
-    # ---- end to end through the batched host API, pinned buffers, copies inside the timed region
-    Fe = min(a.e2e_frames, F)
-    ht = batch.pinned_empty((Fe, H, W, 3), np.float32)
-    hr = batch.pinned_empty((Fe, H, W, 3), np.float32)
-    ho = batch.pinned_empty((Fe, H, W, 3), np.float64)
-    ht[...] = tgt[:Fe].cpu().numpy()
-    hr[...] = ref[:Fe].cpu().numpy()
-    rot_e2e = all_rot[rank::world][:Fe]
-    handle.set_stream(0)
-    batch.idt_frames(ht, hr, BINS, N_ITER, rotations=rot_e2e, out=ho, handle=handle)
-    e2e_steps = max(2, min(a.steps, 5))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        batch.idt_frames(ht, hr, BINS, N_ITER, rotations=rot_e2e, out=ho, handle=handle)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
-    e2e = {"value": world * Fe * npix / 1e6 / e2e_s, "unit": "Mpix/s", "h2d_bytes_per_step": int(2 * Fe * npix * 12),
-           "d2h_bytes_per_step": int(Fe * npix * 24), "frames_per_step": Fe, "ms_per_step": e2e_s * 1e3,
-           "api": "color_transfer_b200.batch.idt_frames -> ct_idt_transfer_host"}
-    # the device-resident result and the host-API result must agree (same kernels)
-    same = bool(np.array_equal(ho[0], out[0].cpu().numpy()))
-
-    # ---- the same frames as uint8 video frames: 3 B/px over PCIe each way
+    # ---- end to end, headline: uint8 video frames through the host API, pinned buffers, copies inside the timed region
+    Fe = max(1, a.e2e_frames)
+    e2e_steps = max(3, min(a.steps, 10))
+    rot_e2e = np.stack([all_rot[(rank + world * k) % len(all_rot)] for k in range(Fe)])
     h8t = batch.pinned_empty((Fe, H, W, 3), np.uint8)
     h8r = batch.pinned_empty((Fe, H, W, 3), np.uint8)
     h8o = batch.pinned_empty((Fe, H, W, 3), np.uint8)
-    h8t[...] = np.rint(ht * 255).astype(np.uint8)
-    h8r[...] = np.rint(hr * 255).astype(np.uint8)
+    t8 = (tgt * 255).round().to(torch.uint8).cpu().numpy()      # the resident frames are exact k/255
+    r8 = (ref * 255).round().to(torch.uint8).cpu().numpy()
+    for k in range(Fe):
+        h8t[k] = t8[k % F]
+        h8r[k] = r8[k % F]
+    handle.set_stream(0)
     batch.idt_frames_u8(h8t, h8r, BINS, N_ITER, rotations=rot_e2e, out=h8o, handle=handle)
     barrier()
     t0 = time.perf_counter()
@@ -429,139 +438,280 @@ def main():
         batch.idt_frames_u8(h8t, h8r, BINS, N_ITER, rotations=rot_e2e, out=h8o, handle=handle)
     barrier()
     u8_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
-    want8 = np.rint(np.clip(ho[0], 0, 1) * 255).astype(np.uint8)
-    e2e_u8 = {"value": world * Fe * npix / 1e6 / u8_s, "unit": "Mpix/s", "h2d_bytes_per_step": int(2 * Fe * npix * 3),
-              "d2h_bytes_per_step": int(Fe * npix * 3), "frames_per_step": Fe, "ms_per_step": u8_s * 1e3,
-              "api": "color_transfer_b200.batch.idt_frames_u8 -> ct_idt_transfer_host_u8 (uint8 frames in and out)",
-              "matches_float_path_bytes": float(np.mean(h8o[0] == want8))}
+    e2e = {"value": world * Fe * npix / 1e6 / u8_s, "unit": "Mpix/s", "h2d_bytes_per_step": int(2 * Fe * npix * 3),
+           "d2h_bytes_per_step": int(Fe * npix * 3), "frame_pairs_per_step": Fe, "steps": e2e_steps, "ms_per_step": u8_s * 1e3,
+           "api": "color_transfer_b200.batch.idt_frames_u8 -> ct_idt_transfer_host_u8 (pinned uint8 frames in and out; "
+                  "decode / encode fused into the kernels that read / write them)",
+           "algorithmic_bytes_per_pixel": IDT_BYTES_PER_PIXEL_U8}
+    # the uint8 path must give exactly the bytes of "device-resident float32 frames -> float64 -> quantise"
+    want8 = np.rint(np.clip(out[0].cpu().numpy(), 0, 1) * 255).astype(np.uint8)
+    e2e["matches_float_path_bytes"] = float(np.mean(h8o[0] == want8))
+    del t8, r8
 
-    extras = {}
-    if not a.no_extras and rank == 0:
-        extras = linear_extras(torch, device, synth, _cabi, handle, dev, peak)
+    # ---- the same through the float API: pinned float32 frames in, the reference's float64 result out
+    Ff = min(8, F)
+    ht = batch.pinned_empty((Ff, H, W, 3), np.float32)
+    hr = batch.pinned_empty((Ff, H, W, 3), np.float32)
+    ho = batch.pinned_empty((Ff, H, W, 3), np.float64)
+    ht[...] = tgt[:Ff].cpu().numpy()
+    hr[...] = ref[:Ff].cpu().numpy()
+    rot_f = all_rot[rank::world][:Ff]
+    batch.idt_frames(ht, hr, BINS, N_ITER, rotations=rot_f, out=ho, handle=handle)
+    f_steps = max(2, min(a.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(f_steps):
+        batch.idt_frames(ht, hr, BINS, N_ITER, rotations=rot_f, out=ho, handle=handle)
+    barrier()
+    f_s = max_over_ranks(time.perf_counter() - t0) / f_steps
+    e2e_float = {"value": world * Ff * npix / 1e6 / f_s, "unit": "Mpix/s", "h2d_bytes_per_step": int(2 * Ff * npix * 12),
+                 "d2h_bytes_per_step": int(Ff * npix * 24), "frame_pairs_per_step": Ff, "ms_per_step": f_s * 1e3,
+                 "api": "color_transfer_b200.batch.idt_frames -> ct_idt_transfer_host (float32 in, float64 out)"}
+    same = bool(np.array_equal(ho[0], out[0].cpu().numpy()))
+    host_dma = host_dma_ceiling(ctx, ht, ho)
+    # the video path moves 6 B/px in and 3 B/px out: its host-to-device stream against what the box gives all ranks
+    e2e["h2d_GBps_aggregate"] = world * e2e["h2d_bytes_per_step"] / u8_s / 1e9
+    e2e["frac_of_host_h2d"] = (e2e["h2d_GBps_aggregate"] / host_dma["h2d_only_GBps_aggregate"]) if "h2d_only_GBps_aggregate" in host_dma else None
+    del ht, hr, ho, h8t, h8r, h8o
+
+    # ---- device-resident uint8 frames (what the video path runs between the copies)
+    t8d, r8d = (tgt * 255).round().to(torch.uint8), (ref * 255).round().to(torch.uint8)
+    o8d = torch.empty_like(t8d)
+    for _ in range(2):
+        device.idt_transfer(t8d, r8d, my_rot, BINS, N_ITER, out=o8d, handle=handle)
+    barrier()
+    e0.record()
+    for _ in range(P):
+        device.idt_transfer(t8d, r8d, my_rot, BINS, N_ITER, out=o8d, handle=handle)
+    e1.record()
+    barrier()
+    ms8 = max_over_ranks(e0.elapsed_time(e1)) / P
+    value_u8 = {"value": world * F * npix / 1e6 / (ms8 / 1e3), "unit": "Mpix/s", "ms_per_pass": ms8,
+                "frac_of_hbm": IDT_BYTES_PER_PIXEL_U8 * npix * F / (ms8 / 1e3) / 1e9 / peak,
+                "note": "device-resident uint8 frames in and out, 243 algorithmic B/px"}
+    del t8d, r8d, o8d, tgt, ref, out
+    torch.cuda.empty_cache()
+
+    linear = rowshard = extras = None
+    if not a.no_extras:
+        linear = linear_section(a, ctx)
+        if world > 1:
+            rowshard = rowshard_section(a, ctx)
+        if rank == 0:
+            extras = single_pair_section(ctx)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        v, wall, _ = cpu_oracle_throughput(H, W, 1, 2)      # two full frame pairs: ~12 s of CPU work
-        cpu = {"value": v, "unit": "Mpix/s", "cores": 1, "kind": "port",
-               "sample": f"two {W}x{H} frame pairs of the workload (of the {F} per step), float32 in, bins={BINS}, "
-                         f"n_iter={N_ITER}, single process ({wall:.1f} s); numpy oracle port of methods/iterative.py"}
+        np.random.seed(42)
+        pool = CpuPool(1)
+        vals, wall = [], 0.0
+        for s in range(2):                       # two full frame pairs: ~12 s of CPU work
+            v, w_, _ = pool.step(H, W, 2000 + s, draw_rotations_np(1))
+            vals.append(v)
+            wall += w_
+        cpu = {"value": sum(vals) / len(vals), "unit": "Mpix/s", "cores": 1, "kind": "port",
+               "sample": f"two {W}x{H} uint8 frame pairs of the workload (of the {F * P} per step): decode, numpy oracle port of "
+                         f"methods/iterative.py (bins={BINS}, n_iter={N_ITER}), encode; single process ({wall:.1f} s)"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": a.steps,
-                "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, F),
-                "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu, "host_api_matches_device_api": same, "extras": extras}
+                "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a),
+                "frame_pairs_per_step": F * P * world, "resident_frame_pairs_per_rank": F, "passes_per_step": P,
+                "timed_region_s": ms_total / 1e3,
+                "clocks": clocks, "e2e": e2e, "e2e_float": e2e_float, "host_dma": host_dma, "value_u8": value_u8,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "host_api_matches_device_api": same, "linear": linear, "rowshard": rowshard, "extras": extras}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_rowshard(a, torch, dist, device, synth, _cabi, handle, dev, world, rank, barrier, max_over_ranks):
+def host_dma_ceiling(ctx, pinned_a, pinned_b):
+    """What the host <-> device DMA of this box gives all ranks TOGETHER: every rank copies pinned host
+    memory to its GPU (h2d_only), back (d2h_only), and both at once on two streams (both_*), no kernels.
+    An end-to-end number at N GPUs cannot exceed bytes-per-pixel over this."""
+    torch, dev = ctx["torch"], ctx["dev"]
+    try:
+        ha = torch.from_numpy(pinned_a.reshape(-1).view("uint8"))
+        hb = torch.from_numpy(pinned_b.reshape(-1).view("uint8"))
+        n = min(ha.numel(), hb.numel(), 1 << 29)
+        ha, hb = ha[:n], hb[:n]
+        da = torch.empty(n, dtype=torch.uint8, device=dev)
+        db = torch.empty(n, dtype=torch.uint8, device=dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        reps = 4
+
+        def run(h2d, d2h):
+            for _ in range(reps):
+                if h2d:
+                    with torch.cuda.stream(s_in):
+                        da.copy_(ha, non_blocking=True)
+                if d2h:
+                    with torch.cuda.stream(s_out):
+                        hb.copy_(db, non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+
+        def timed(h2d, d2h):
+            run(h2d, d2h)
+            ctx["barrier"]()
+            t0 = time.perf_counter()
+            run(h2d, d2h)
+            ctx["barrier"]()
+            dt = ctx["max_over_ranks"](time.perf_counter() - t0)
+            return ctx["world"] * reps * n / dt / 1e9
+        return {"h2d_only_GBps_aggregate": timed(True, False), "d2h_only_GBps_aggregate": timed(False, True),
+                "both_GBps_aggregate_each_way": timed(True, True), "bytes_per_copy": int(n), "ranks": ctx["world"],
+                "note": "pinned copies on every rank at the same time, no kernels; wall clock, max over ranks"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)}
+
+
+def linear_section(a, ctx):
+    """configs[2]: `--linear-pairs` (1035) pairs of 960x540 float32 per rank, frame-parallel (no collective):
+    Reinhard f32 -> f32, MKL and CCS f32 -> f64, smooth-field and i.i.d.-uniform frames, ONE device-resident
+    call per method; CUDA events, max over ranks; value = all ranks' pixels / that time."""
+    torch, device, synth, _cabi, handle, dev = ctx["torch"], ctx["device"], ctx["synth"], ctx["_cabi"], ctx["handle"], ctx["dev"]
+    world, rank, peak = ctx["world"], ctx["rank"], ctx["peak"]
+    B, H, W = a.linear_pairs, 540, 960
+    res = {"config": {"workload": "configs[2]: batch of synthetic 960x540 stereopairs, linear transfer, frame-parallel",
+                      "pairs_per_rank": B, "shape": [H, W, 3], "input_dtype": "float32", "parallelism": f"frame-parallel x{world}, no collective",
+                      "l2": "batch working set (6.4 GB per eye) exceeds the L2"},
+           "unit": "Mpix/s"}
+    methods = (("reinhard_f32", _cabi.CT_REINHARD, 48, torch.float32), ("mkl_f32_to_f64", _cabi.CT_MKL_MK, 60, torch.float64),
+               ("ccs_f32_to_f64", _cabi.CT_CCS, 60, torch.float64))
+    for dist_name, stress in (("smooth-field+noise", False), ("uniform-noise", True)):
+        tgt, ref = synth.frame_pairs_cuda(B, H, W, 1000 + rank, dev, stress=stress)
+        for name, method, bpp, odt in methods:
+            if stress and method == _cabi.CT_CCS:
+                continue
+            dst = torch.empty((B, H, W, 3), dtype=odt, device=dev)
+            for _ in range(2):
+                device.linear_transfer(method, tgt, ref, out=dst, handle=handle)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ctx["barrier"]()
+            reps = 5
+            e0.record()
+            for _ in range(reps):
+                device.linear_transfer(method, tgt, ref, out=dst, handle=handle)
+            e1.record()
+            ctx["barrier"]()
+            ms = ctx["max_over_ranks"](e0.elapsed_time(e1)) / reps
+            gbps = bpp * B * H * W / (ms / 1e3) / 1e9           # per GPU
+            res[f"{name}/{dist_name}"] = {"value": world * B * H * W / 1e6 / (ms / 1e3), "ms_per_batch": ms,
+                                          "algorithmic_bytes_per_pixel": bpp, "per_gpu_GBps": gbps, "frac_of_hbm": gbps / peak}
+            del dst
+        del tgt, ref
+        torch.cuda.empty_cache()
+    res["value"] = res["reinhard_f32/smooth-field+noise"]["value"]
+    res["metric"] = "stereopair Mpix/s (Reinhard, 1035 x 960x540 float32 pairs per rank, frame-parallel)"
+    return res
+
+
+def rowshard_section(a, ctx):
     """configs[4]: one side x side float32 pair, contiguous row blocks per rank (strong scaling).
-    IDT: 1 + n_iter MIN all-reduces of 6 int64 keys, n_iter SUM all-reduces of 6*bins int64 counts;
-    MKL / Reinhard: one all-gather of 2x10 raw moments.  Device-resident shards, CUDA events,
-    max over ranks."""
+    IDT: 1 + n_iter MIN all-reduces of 6 int64 keys and n_iter SUM all-reduces of 6*bins int64 counts;
+    MKL / Reinhard: one all-gather of 2x10 raw moments.  Device-resident shards, CUDA events, max over
+    ranks.  Before the timing, the same drivers run on a 4096x4096 pair of the same generator and every
+    rank compares its rows with the UNSHARDED result it computes itself: bit-identical histogram counts and
+    output for IDT, <= 1e-12 for MKL, <= 2e-6 (float32) for Reinhard."""
     import numpy as np
     from color_transfer_b200 import sharded
-    side = a.side
-    r0, r1 = sharded.row_partition(side, world, rank)
-    rows = r1 - r0
-    # every rank generates only its rows (seeded per row block so the pair is the same for any world size)
-    tgt, ref = synth.frame_pairs_cuda(1, rows, side, 3000 + r0, dev)
-    tgt, ref = tgt[0], ref[0]
+    torch, dist, device, synth, _cabi, handle, dev = (ctx[k] for k in ("torch", "dist", "device", "synth", "_cabi", "handle", "dev"))
+    world, rank, peak = ctx["world"], ctx["rank"], ctx["peak"]
+    comm = sharded.Comm()
     np.random.seed(42)
     rot = sharded.predraw_rotations(1, N_ITER)[0]
-    comm = sharded.Comm()
-    results = {}
-    peak, _ = measured_peaks()
+    drot = torch.from_numpy(rot[None]).to(dev)
+
+    # ---- parity: 4096 x 4096, every rank holds the whole pair and its own row block
+    side_p = 4096
+    tp, rp = synth.frame_pairs_cuda(1, side_p, side_p, 3000, dev)
+    tp, rp = tp[0], rp[0]
+    p0, p1 = sharded.row_partition(side_p, world, rank)
+    full_counts = []
+    st = device.IdtStages(tp, rp, drot, BINS, N_ITER, handle=handle)
+    full = st.run(between=lambda n, x: full_counts.append(x.clone()) if n == "counts" else None, fuse_lut=False)[0]
+    part_counts = []
+
+    def between(name, tensor):
+        if name == "keys":
+            comm.min_(tensor)
+        else:
+            comm.sum_(tensor)
+            part_counts.append(tensor.clone())
+
+    backend = sharded.CudaIdtBackend(tp[p0:p1].contiguous(), rp[p0:p1].contiguous(), rot, BINS, N_ITER, handle)
+    part = backend.run(between)
+    backend.finish()
+    counts_ok = len(part_counts) == len(full_counts) and all(torch.equal(x, y) for x, y in zip(part_counts, full_counts))
+    idt_ok = bool(torch.equal(part, full[p0:p1]))
+    mkl = sharded.linear_transfer_sharded(_cabi.CT_MKL_MK, tp[p0:p1].contiguous(), rp[p0:p1].contiguous(), comm=comm, handle=handle)
+    mkl_err = float((mkl - device.linear_transfer(_cabi.CT_MKL_MK, tp, rp, handle=handle)[p0:p1]).abs().max())
+    rei = sharded.linear_transfer_sharded(_cabi.CT_REINHARD, tp[p0:p1].contiguous(), rp[p0:p1].contiguous(), comm=comm, handle=handle)
+    rei_err = float((rei - device.linear_transfer(_cabi.CT_REINHARD, tp, rp, handle=handle)[p0:p1]).abs().max())
+    ok_local = counts_ok and idt_ok and mkl_err <= 1e-12 and rei_err <= 2e-6
+    flag = torch.tensor([1 if ok_local else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    errs = torch.tensor([mkl_err, rei_err], dtype=torch.float64, device=dev)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    parity = {"parity_ok": bool(flag.item() == 1), "pair": [side_p, side_p, 3], "idt_counts_bit_identical": counts_ok,
+              "idt_output_bit_identical": idt_ok, "mkl_max_abs": float(errs[0]), "reinhard_f32_max_abs": float(errs[1]),
+              "against": "the unsharded single-GPU result, computed by every rank"}
+    del tp, rp, full, part, mkl, rei, st, backend
+    torch.cuda.empty_cache()
+
+    # ---- timing: side x side, every rank generates only its rows
+    side = a.rowshard_side
+    r0, r1 = sharded.row_partition(side, world, rank)
+    rows = r1 - r0
+    tgt, ref = synth.frame_pairs_cuda(1, rows, side, 3000 + r0, dev)
+    tgt, ref = tgt[0], ref[0]
     npix = side * side
 
     def timed(fn, reps):
         for _ in range(2):
             fn()
-        barrier()
+        ctx["barrier"]()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
             fn()
         e1.record()
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1)) / reps
+        ctx["barrier"]()
+        return ctx["max_over_ranks"](e0.elapsed_time(e1)) / reps
 
     backend = sharded.CudaIdtBackend(tgt, ref, rot, BINS, N_ITER, handle)
-
-    def idt():
-        def between(name, tensor):
-            comm.min_(tensor) if name == "keys" else comm.sum_(tensor)
-        backend.run(between)
-
-    ms = timed(idt, max(2, min(a.steps, 5)))
-    results["idt"] = {"ms_per_pair": ms, "Mpix/s": npix / 1e6 / (ms / 1e3),
-                      "frac_of_hbm_aggregate": IDT_BYTES_PER_PIXEL_F32 * npix / (ms / 1e3) / 1e9 / (peak * world),
-                      "collectives_per_pair": 1 + 2 * N_ITER - 1 + 1}
+    calls0 = comm.calls
+    backend.run(lambda name, tensor: comm.min_(tensor) if name == "keys" else comm.sum_(tensor))
+    collectives_idt = comm.calls - calls0
+    ms = timed(lambda: backend.run(lambda name, tensor: comm.min_(tensor) if name == "keys" else comm.sum_(tensor)), 5)
+    res = {"config": {"workload": f"configs[4]: single {side}x{side} float32 stereopair row-sharded across {world} GPUs with NCCL "
+                                  "all-reduce of range keys / histogram counts / moments",
+                      "rows_per_rank": rows, "bins": BINS, "n_iter": N_ITER},
+           "scaling": "strong", "unit": "Mpix/s", "parity": parity, "parity_ok": parity["parity_ok"],
+           "idt": {"ms_per_pair": ms, "value": npix / 1e6 / (ms / 1e3), "collectives": collectives_idt,
+                   "frac_of_hbm_aggregate": IDT_BYTES_PER_PIXEL_F32 * npix / (ms / 1e3) / 1e9 / (peak * world)}}
+    del backend
     for name, code, bpp in (("mkl", _cabi.CT_MKL_MK, 60), ("reinhard", _cabi.CT_REINHARD, 48)):
-        ms = timed(lambda: sharded.linear_transfer_sharded(code, tgt, ref, comm=comm, handle=handle), max(2, min(a.steps, 5)))
-        results[name] = {"ms_per_pair": ms, "Mpix/s": npix / 1e6 / (ms / 1e3),
-                         "frac_of_hbm_aggregate": bpp * npix / (ms / 1e3) / 1e9 / (peak * world), "collectives_per_pair": 1}
-    if rank == 0:
-        emit({"metric": "stereopair Mpix/s (one %dx%d pair, row-sharded)" % (side, side), "unit": "Mpix/s",
-              "n_gpus": world, "scaling": "strong", "value": results["idt"]["Mpix/s"], "data": "synthetic",
-              "config": {"workload": "configs[4]: single %dx%d float32 stereopair row-sharded with NCCL all-reduces" % (side, side),
-                         "rows_per_rank": rows, "bins": BINS, "n_iter": N_ITER}, "results": results})
+        ms = timed(lambda: sharded.linear_transfer_sharded(code, tgt, ref, comm=comm, handle=handle), 5)
+        res[name] = {"ms_per_pair": ms, "value": npix / 1e6 / (ms / 1e3), "collectives": 1,
+                     "frac_of_hbm_aggregate": bpp * npix / (ms / 1e3) / 1e9 / (peak * world)}
+    res["ms_per_pair"] = res["idt"]["ms_per_pair"]
+    res["frac_of_hbm_aggregate"] = res["idt"]["frac_of_hbm_aggregate"]
+    res["collectives"] = collectives_idt
+    del tgt, ref
+    torch.cuda.empty_cache()
+    return res
 
 
-def linear_extras(torch, device, synth, _cabi, handle, dev, peak):
-    """Secondary numbers for the linear transfers (configs[2] shape: 960x540 float32 pairs)."""
-    out = {}
-    B, H, W = 64, 540, 960
-    tgt, ref = synth.frame_pairs_cuda(B, H, W, 1000, dev)
-    for name, method, bpp in (("reinhard_f32", _cabi.CT_REINHARD, 48), ("mkl_f32_to_f64", _cabi.CT_MKL_MK, 60)):
-        dst = torch.empty((B, H, W, 3), dtype=torch.float32 if method == _cabi.CT_REINHARD else torch.float64, device=dev)
-        for _ in range(3):
-            device.linear_transfer(method, tgt, ref, out=dst, handle=handle)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        reps = 10
-        for _ in range(reps):
-            device.linear_transfer(method, tgt, ref, out=dst, handle=handle)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        gbps = bpp * B * H * W / (ms / 1e3) / 1e9
-        out[name] = {"Mpix/s": B * H * W / 1e6 / (ms / 1e3), "ms_per_batch": ms, "pairs": B, "shape": [H, W, 3],
-                     "algorithmic_GBps": gbps, "frac_of_hbm": gbps / peak,
-                     "note": "batch working set 1.2-2.0 GB, larger than L2"}
-    # configs[2] as named: the whole batch of 1035 pairs of 960x540 float32 in one call, primary
-    # (smooth field) and stress (i.i.d. uniform) distributions
-    del tgt, ref, dst
-    B2 = 1035
-    full = {}
-    for dist_name, stress in (("smooth-field+noise", False), ("uniform-noise", True)):
-        tgt, ref = synth.frame_pairs_cuda(B2, H, W, 1000, dev, stress=stress)
-        for name, method, bpp in (("reinhard_f32", _cabi.CT_REINHARD, 48), ("mkl_f32_to_f64", _cabi.CT_MKL_MK, 60)):
-            if stress and method != _cabi.CT_REINHARD:
-                continue
-            dst = torch.empty((B2, H, W, 3), dtype=torch.float32 if method == _cabi.CT_REINHARD else torch.float64, device=dev)
-            device.linear_transfer(method, tgt, ref, out=dst, handle=handle)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(3):
-                device.linear_transfer(method, tgt, ref, out=dst, handle=handle)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 3
-            gbps = bpp * B2 * H * W / (ms / 1e3) / 1e9
-            full[f"{name}/{dist_name}"] = {"Mpix/s": B2 * H * W / 1e6 / (ms / 1e3), "ms_per_batch": ms,
-                                           "algorithmic_GBps": gbps, "frac_of_hbm": gbps / peak}
-            del dst
-        del tgt, ref
-    out["config2_1035_pairs_960x540"] = full
-    # configs[0] / configs[1] shape: one 1080x860 float64 pair (L2-resident, launch-latency regime)
+def single_pair_section(ctx):
+    """configs[0] / configs[1] shape: one 1080x860 float64 pair (L2-resident, launch-latency regime) on the
+    device, and the reference's own stereo pair through the reference-facing numpy functions."""
     import numpy as np
-    from color_transfer_b200 import batch
+    torch, device, synth, _cabi, batch, handle, dev = (ctx[k] for k in ("torch", "device", "synth", "_cabi", "batch", "handle", "dev"))
+    out = {}
     t64, r64 = synth.frame_pairs_cuda(1, 860, 1080, 964, dev, dtype=torch.float64)
     np.random.seed(42)
     rot = torch.from_numpy(batch.draw_rotations(N_ITER)[None]).to(dev)

@@ -72,6 +72,8 @@ SIGNATURES = {
                                                   ctypes.c_int32]),
     "ct_idt_transfer_host_u8": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
                                                _P, ctypes.c_int32, ctypes.c_int32]),
+    "ct_profile_enable": (ctypes.c_int, [_P, ctypes.c_int]),
+    "ct_profile_read": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32]),
     "ct_idt_key_of": (ctypes.c_int64, [ctypes.c_double]),
     "ct_idt_value_of": (ctypes.c_double, [ctypes.c_int64]),
     "ct_idt_keys_init": (ctypes.c_int, [_P, _P, ctypes.c_int64]),
@@ -120,7 +122,7 @@ class CtError(RuntimeError):
         self.message = message
 
 
-_DTYPES = {np.dtype(np.float32): CT_F32, np.dtype(np.float64): CT_F64, np.dtype(np.uint8): CT_U8}
+_DTYPES = {np.dtype(np.float32): CT_F32, np.dtype(np.float64): CT_F64}   # uint8 arrays are promoted like the reference's float math; uint8 FRAMES go through batch.*_u8
 
 
 def batch_from_pointer(ptr, npix, dtype, layout=CT_HWC, count=1, image_stride=0, plane_stride=0):
@@ -189,6 +191,21 @@ class Handle:
 
     def synchronize(self):
         self.check(self.lib.ct_synchronize(self.h))
+
+    PROF_NAMES = {1: "seed", 2: "ranges_target", 3: "ranges_reference", 4: "hist", 5: "remap"}
+
+    def profile(self, on):
+        """Start / stop per-launch timing of the fused IDT driver (see ct_profile_enable)."""
+        self.check(self.lib.ct_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self, max_entries=4096):
+        """[(name, ms), ...] of the launches since the last read, in launch order."""
+        ids = (ctypes.c_int32 * max_entries)()
+        ms = (ctypes.c_float * max_entries)()
+        n = self.lib.ct_profile_read(self.h, ids, ms, max_entries)
+        if n < 0:
+            self.check(n)
+        return [(self.PROF_NAMES.get(ids[i], str(ids[i])), float(ms[i])) for i in range(n)]
 
     @property
     def launches(self):

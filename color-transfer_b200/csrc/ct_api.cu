@@ -63,12 +63,8 @@ int ensure_scratch(ct_context *h, int pairs) {
     CT_TRY(grow(h, &h->xform, &have_x, (size_t)cap * CT_XFORM_DOUBLES, false));
     CT_TRY(grow(h, &h->sums, &have_s, (size_t)cap * 2 * CT_MOMENT_DOUBLES, false));
     CT_TRY(grow(h, &h->status, &have_st, (size_t)cap, true));
+    // (the pinned bounce buffers of ct_host_copy.h do not depend on the pair count: they stay)
     if (h->host_status) cudaFreeHost(h->host_status);
-    for (int d = 0; d < 2; ++d)
-        for (int i = 0; i < 2; ++i) {
-            if (h->bounce[d][i]) cudaFreeHost(h->bounce[d][i]);
-            if (h->bounce_done[d][i]) cudaEventDestroy(h->bounce_done[d][i]);
-        }
     h->host_status = nullptr;
     CT_CUDA(h, cudaMallocHost(&h->host_status, sizeof(int) * (size_t)cap));
     h->scratch_pairs = cap;
@@ -166,6 +162,7 @@ static int idt_run(ct_context *h, const ct_batch *target, const ct_batch *refere
     CT_CUDA(h, cudaMemsetAsync(L.counts, 0, sizeof(uint64_t) * (size_t)B * 6 * bins, h->stream));
     CT_CUDA(h, cudaMemsetAsync(st, 0, sizeof(int32_t) * (size_t)B, h->stream));
     const int64_t keys_stride = (int64_t)(n_iter + 1) * CT_IDT_KEYS, rot_stride = (int64_t)n_iter * 9;
+    prof_mark(h, CT_PROF_START);
     // iteration 0 needs the target's range; the reference never changes, so its range under
     // EVERY rotation is taken in the same single pass over it.  One seed launch (which also sets the
     // keys to +inf) and one screened pass over both images.
@@ -255,6 +252,7 @@ void ct_destroy(ct_handle h) {
             if (h->bounce[d][i]) cudaFreeHost(h->bounce[d][i]);
             if (h->bounce_done[d][i]) cudaEventDestroy(h->bounce_done[d][i]);
         }
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         if (h->side[i]) cudaStreamDestroy(h->side[i]);
         if (h->join[i]) cudaEventDestroy(h->join[i]);
@@ -277,6 +275,30 @@ int ct_synchronize(ct_handle h) {
     if (!h) return CT_E_INVALID;
     CT_CUDA(h, cudaStreamSynchronize(h->stream));
     return CT_OK;
+}
+
+int ct_profile_enable(ct_handle h, int on) {
+    if (!h) return CT_E_INVALID;
+    h->prof_on = on != 0;
+    h->prof_n = 0;
+    return CT_OK;
+}
+
+int ct_profile_read(ct_handle h, int32_t *ids, float *ms, int32_t max) {
+    if (!h || !ids || !ms || max < 0) return CT_E_INVALID;
+    int n = 0;
+    if (h->prof_n >= 2) {
+        CT_CUDA(h, cudaEventSynchronize(h->prof_ev[h->prof_n - 1]));
+        for (size_t i = 1; i < h->prof_n && n < max; ++i) {
+            if (h->prof_id[i] == CT_PROF_START) continue;   // the gap between two driver calls
+            float t = 0.0f;
+            CT_CUDA(h, cudaEventElapsedTime(&t, h->prof_ev[i - 1], h->prof_ev[i]));
+            ids[n] = h->prof_id[i];
+            ms[n++] = t;
+        }
+    }
+    h->prof_n = 0;
+    return n;
 }
 
 int ct_sm_count(ct_handle h) { return h ? h->sm_count : 0; }
@@ -350,9 +372,12 @@ int ct_linear_transfer(ct_handle h, int method, const ct_batch *target, const ct
             CT_CUDA(h, cudaEventCreateWithFlags(&h->join[i], cudaEventDisableTiming));
         }
     }
-    // blocks_for() never launches more than 8 waves of 4 CTAs per SM: one such region per side stream
-    const size_t region = (size_t)h->sm_count * 4 * 8 * 9;
+    // one partials region per side stream: blocks_for() never launches more than 8 waves of 4 CTAs per SM
+    // for both images of a chunk, and never fewer than one CTA per image (tiny images, many pairs)
+    size_t region = (size_t)h->sm_count * 4 * 8 * 9;
+    if ((size_t)chunk * 2 * 9 > region) region = (size_t)chunk * 2 * 9;
     CT_TRY(ensure_partials(h, 2 * region));
+    h->partials_region = region;
     CT_TRY(ensure_scratch(h, target->count > 2 * chunk ? target->count : 2 * chunk));
     cudaStream_t user = h->stream;
     CT_CUDA(h, cudaEventRecord(h->fork, user));
@@ -376,6 +401,7 @@ int ct_linear_transfer(ct_handle h, int method, const ct_batch *target, const ct
     h->stream = user;
     h->ticket_base = 0;
     h->partials_base = 0;
+    h->partials_region = 0;
     for (int i = 0; i < 2; ++i) {
         CT_CUDA(h, cudaEventRecord(h->join[i], h->side[i]));
         CT_CUDA(h, cudaStreamWaitEvent(user, h->join[i], 0));

@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "ct_common.cuh"
 
 struct ct_context {
@@ -31,6 +33,12 @@ struct ct_context {
     size_t ws_bytes = 0;
     void *stage = nullptr;
     size_t stage_bytes = 0;
+    // optional per-launch timing of the fused IDT driver (ct_profile_enable / ct_profile_read)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_id;
+    size_t prof_n = 0;
+
     double *u8_tmp = nullptr;   // inside ws: float64 result of a one-iteration IDT on uint8 frames before it is encoded
 
     // K4 screen: pixels with |x0|+|x1|+|x2| above this take the exact fp64 path (CT_RANGES_BOUND)
@@ -54,6 +62,7 @@ struct ct_context {
     cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
     int ticket_base = 0;        // first ticket and first partials double a moments launch may use
     size_t partials_base = 0;   // (one region per side stream)
+    size_t partials_region = 0; // doubles per region while a chunked batch is in flight, else 0
 };
 
 namespace ct {
@@ -81,6 +90,19 @@ inline int fail(ct_context *h, int code, const char *fmt, ...) {
         int rc__ = (expr);            \
         if (rc__ != CT_OK) return rc__; \
     } while (0)
+
+// record a timing mark on the handle's stream: the span since the previous mark belongs to launch `id`
+inline void prof_mark(ct_context *h, int id) {
+    if (!h->prof_on) return;
+    if (h->prof_n == h->prof_ev.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        h->prof_ev.push_back(e);
+        h->prof_id.push_back(0);
+    }
+    h->prof_id[h->prof_n] = id;
+    cudaEventRecord(h->prof_ev[h->prof_n++], h->stream);
+}
 
 inline int src_kind(const ct_batch *b) { return b->dtype * 2 + b->layout; }
 inline size_t elem_size(int dtype) { return dtype == CT_F32 ? 4 : (dtype == CT_U8 ? 1 : 8); }

@@ -1059,6 +1059,7 @@ int launch_ranges_pair(ct_context *h, const ct_batch *target, const ct_batch *re
         ranges_seed_kernel<<<dim3((unsigned)seed_ctas, count, 2), kThreads, 0, h->stream>>>(a);
         h->launches++;
         CT_CUDA(h, cudaGetLastError());
+        prof_mark(h, CT_PROF_SEED);
         for (int z = 0; z < 2; ++z) {
             if (!imgs[z]) continue;
             a.which = z;
@@ -1078,6 +1079,7 @@ int launch_ranges_pair(ct_context *h, const ct_batch *target, const ct_batch *re
             CT_TRY(rc);
             h->launches++;
             CT_CUDA(h, cudaGetLastError());
+            prof_mark(h, z == 0 ? CT_PROF_RANGES_TARGET : CT_PROF_RANGES_REFERENCE);
         }
     }
     return CT_OK;
@@ -1175,6 +1177,7 @@ int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt
     else hist_kernel<false><<<dim3(nblk, B), kThreads, smem, h->stream>>>(a);
     h->launches++;
     CT_CUDA(h, cudaGetLastError());
+    prof_mark(h, CT_PROF_HIST);
     return CT_OK;
 }
 
@@ -1242,6 +1245,7 @@ int launch_remap(ct_context *h, const ct_idt_stage *s, const ct_batch *dst, int 
     }
     h->launches++;
     CT_CUDA(h, cudaGetLastError());
+    prof_mark(h, CT_PROF_REMAP);
     return CT_OK;
 }
 

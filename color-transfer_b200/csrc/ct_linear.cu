@@ -378,7 +378,9 @@ int launch_moments(ct_context *h, const ct_batch *a, const ct_batch *b, int lab,
     if (b && b->npix > npix_max) npix_max = b->npix;
     // a single pair gets exactly one resident wave (short fixed-order combine); batches whole waves
     const int nblk = blocks_for(h, npix_max, 2, (int64_t)B * nimg, lab ? CT_LAB_CTAS_PER_SM : 3, 1);
-    // (a chunked batch pre-sizes both buffers: growing them here would free memory in use)
+    // (a chunked batch pre-sizes both buffers: growing them here would free memory the other side stream is using)
+    if (h->partials_region && (size_t)B * nimg * nblk * 9 > h->partials_region)
+        return fail(h, CT_E_NOMEM, "moments partials region too small for %d pairs x %d blocks", B, nblk);
     CT_TRY(ensure_partials(h, h->partials_base + (size_t)B * nimg * nblk * 9));
     CT_TRY(ensure_scratch(h, h->ticket_base + B));
     MomentsArgs m{};

@@ -13,6 +13,13 @@ import numpy as np
 
 
 def frame_pair(h, w, seed, dtype=np.float32, stress=False):
+    """(target, reference) as k/255 in ``dtype``."""
+    target, reference = frame_pair_u8(h, w, seed, stress)
+    return (target / 255.0).astype(dtype), (reference / 255.0).astype(dtype)
+
+
+def frame_pair_u8(h, w, seed, stress=False):
+    """(target, reference) as uint8 video frames [H,W,3]."""
     rng = np.random.default_rng(seed)
     if stress:
         g = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
@@ -30,7 +37,7 @@ def frame_pair(h, w, seed, dtype=np.float32, stress=False):
     reference = np.roll(g, 16, axis=1)
     gain, gamma = rng.uniform(0.7, 1.3, 3), rng.uniform(0.7, 1.3, 3)
     target = np.clip(255.0 * gain * (g / 255.0) ** gamma, 0, 255).astype(np.uint8)
-    return (target / 255.0).astype(dtype), (reference / 255.0).astype(dtype)
+    return target, reference
 
 
 def frame_pairs_cuda(count, h, w, seed, device, dtype=None, stress=False):

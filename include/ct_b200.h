@@ -89,6 +89,15 @@ int ct_sm_count(ct_handle h);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t ct_launch_count(ct_handle h);
 
+/* Per-launch device times of the fused IDT driver (bench.py's roofline): while enabled, every launch of
+ * ct_idt_transfer is followed by a CUDA event on the handle's stream.  ct_profile_read waits for the last
+ * one and returns up to `max` (id, milliseconds) pairs in launch order - the time between consecutive
+ * events - and clears the list.  ids: CT_PROF_*. */
+enum { CT_PROF_START = 0, CT_PROF_SEED = 1, CT_PROF_RANGES_TARGET = 2, CT_PROF_RANGES_REFERENCE = 3,
+       CT_PROF_HIST = 4, CT_PROF_REMAP = 5 };
+int ct_profile_enable(ct_handle h, int on);
+int ct_profile_read(ct_handle h, int32_t *ids, float *ms, int32_t max);
+
 /* ------------------------------------------------------------------ linear transfers */
 /* Raw moments of one image about a fixed shift K (0.5 per RGB channel, (50,0,0) in Lab):
  * sums[b] = { n, S(x-K)[3], S(x-K)(x-K)^T as 00,01,02,11,12,22 }.  They are exactly additive

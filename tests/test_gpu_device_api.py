@@ -207,6 +207,22 @@ def test_large_batches_run_chunked_on_two_streams(mods):
     torch.cuda.synchronize()
 
 
+def test_many_small_pairs_in_one_chunked_call(mods):
+    """7000 pairs of 96x96 in one device-resident call: the two-stream chunks hold ~3500 pairs each, more
+    than one partial-sum slot per resident CTA - the regions of the two streams must not overlap
+    (each chunk's moments are checked against single-pair calls)."""
+    torch, _cabi, batch, device, sharded, synth, oracle = mods
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    B, H, W = 7000, 96, 96
+    t = torch.rand((B, H, W, 3), generator=gen, device="cuda")
+    r = torch.rand((B, H, W, 3), generator=gen, device="cuda") * 0.8 + 0.1
+    out = device.linear_transfer(_cabi.CT_MKL_MK, t, r)
+    torch.cuda.synchronize()
+    for i in (0, 1, 3471, 3472, 3473, 5000, 6999):
+        one = device.linear_transfer(_cabi.CT_MKL_MK, t[i], r[i])
+        assert float((out[i] - one).abs().max()) < 1e-12, f"pair {i}"
+
+
 def test_reinhard_float32_toes_and_nan(mods):
     """float32 Reinhard: images that live entirely in the linear toes of the gamma / Lab curves
     (the patched rare branches of ct_lab.cuh), and NaN propagation like numpy (a NaN pixel turns the
