@@ -310,5 +310,184 @@ __device__ __forceinline__ void reinhard_group_h(const ReinhardFold &k, const fl
         for (int j = 0; j < 3; ++j) out[i][j] = clip01_nan(out[i][j]);
 }
 
+
+// ------------------------------------------------------------------ the fp32 chain on pixel PAIRS
+// Both Lab kernels were bound by instruction issue and the XU pipe together (round 1: XU 62-68 %,
+// issue 61-67 %, 0.66-0.70 of the HBM roofline).  sm_100 has packed fp32 arithmetic (FFMA2 / FMUL2 /
+// FADD2: two IEEE operations per instruction, same lane throughput), so the chain above is written
+// once more on float2 = (pixel 2i, pixel 2i+1): the same operations in the same order on every lane
+// - results are bit-identical to the scalar functions, which stay for the one-pixel tails - at half
+// the issue slots.  MUFU (lg2 / ex2) and the 3-input minima of the toe tests remain scalar.  With the
+// issue pressure gone all three cube-root seeds can come from the FMA pipe, which leaves the XU pipe
+// with the 12 MUFU of the two gamma curves per pixel.
+using f2 = float2;
+__device__ __forceinline__ f2 splat(float v) { return make_float2(v, v); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 neg2(f2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ f2 lg2_2(f2 a) { return make_float2(lg2_approx(a.x), lg2_approx(a.y)); }
+__device__ __forceinline__ f2 ex2_2(f2 a) { return make_float2(ex2_approx(a.x), ex2_approx(a.y)); }
+__device__ __forceinline__ f2 select_gt(f2 x, float thr, f2 a, f2 b) {   // x > thr ? a : b, per lane
+    return make_float2(x.x > thr ? a.x : b.x, x.y > thr ? a.y : b.y);
+}
+
+template <int P>
+__device__ __forceinline__ float min_of2(const f2 (&x)[P][3]) {
+    float m = min3(x[0][0].x, x[0][0].y, x[0][1].x);
+    m = min3(m, x[0][1].y, x[0][2].x);
+    m = fminf(m, x[0][2].y);
+#pragma unroll
+    for (int i = 1; i < P; ++i) {
+        m = min3(m, x[i][0].x, x[i][0].y);
+        m = min3(m, x[i][1].x, x[i][1].y);
+        m = min3(m, x[i][2].x, x[i][2].y);
+    }
+    return m;
+}
+
+__device__ __forceinline__ f2 rcbrt_fma2(f2 t) {
+    const f2 y = make_float2(__uint_as_float(0x54a23000u - __umulhi(__float_as_uint(t.x), 0x55555556u)),
+                             __uint_as_float(0x54a23000u - __umulhi(__float_as_uint(t.y), 0x55555556u)));
+    const f2 r = fma2(neg2(t), mul2(mul2(y, y), y), splat(1.0f));
+    f2 p = fma2(r, splat(0.1244070650f), splat(0.1453286727f));
+    p = fma2(r, p, splat(0.1728475290f));
+    p = fma2(r, p, splat(0.2222193078f));
+    p = fma2(r, p, splat(0.3333333260f));
+    return fma2(mul2(y, r), p, y);
+}
+__device__ __forceinline__ f2 rcbrt_xu2(f2 t) { return ex2_2(mul2(splat(-0.33333334f), lg2_2(t))); }
+
+template <int P, bool FAST>
+__device__ __forceinline__ void decode_pairs(const f2 (&v)[P][3], f2 (&l)[P][3]) {
+#pragma unroll
+    for (int i = 0; i < P; ++i)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const f2 u = fma2(v[i][c], splat(1.0f / 1.055f), splat(0.055f / 1.055f));
+            const f2 lg = lg2_2(u);
+            l[i][c] = FAST ? ex2_2(mul2(splat(2.4f), lg)) : mul2(mul2(u, u), ex2_2(mul2(splat(0.4f), lg)));
+        }
+    if (min_of2<P>(v) <= CT_THR_DEC_F) {
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) l[i][c] = select_gt(v[i][c], CT_THR_DEC_F, l[i][c], mul2(v[i][c], splat(1.0f / 12.92f)));
+    }
+}
+
+// the scalar CT_XYZ_ROW* evaluate (m0 a + m1 b) + m2 c with plain multiplies and adds that the compiler
+// contracts to fma(m2, c, fma(m1, b, m0 a)); written out here so that both versions round identically
+template <int P, int FMA_SEEDS, bool POLISH>
+__device__ __forceinline__ void xyzf_pairs(const f2 (&l)[P][3], f2 (&f)[P][3]) {
+    f2 t[P][3];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        t[i][0] = fma2(splat((float)(0.180423 / 0.95047)), l[i][2], fma2(splat((float)(0.357580 / 0.95047)), l[i][1], mul2(splat((float)(0.412453 / 0.95047)), l[i][0])));
+        t[i][1] = fma2(splat(0.072169f), l[i][2], fma2(splat(0.715160f), l[i][1], mul2(splat(0.212671f), l[i][0])));
+        t[i][2] = fma2(splat((float)(0.950227 / 1.08883)), l[i][2], fma2(splat((float)(0.119193 / 1.08883)), l[i][1], mul2(splat((float)(0.019334 / 1.08883)), l[i][0])));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const bool fma_seed = c == 1 ? FMA_SEEDS > 0 : (c == 0 ? FMA_SEEDS > 1 : FMA_SEEDS > 2);
+            const f2 z = fma_seed ? rcbrt_fma2(t[i][c]) : rcbrt_xu2(t[i][c]);
+            const f2 zz = mul2(z, z);
+            f2 y = mul2(t[i][c], zz);
+            if (POLISH) y = fma2(fma2(neg2(mul2(y, y)), y, t[i][c]), mul2(zz, splat(0.33333334f)), y);
+            f[i][c] = y;
+        }
+    }
+    if (min_of2<P>(t) <= CT_THR_F_F) {
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) f[i][c] = select_gt(t[i][c], CT_THR_F_F, f[i][c], fma2(splat(7.787f), t[i][c], splat(16.0f / 116.0f)));
+    }
+}
+
+// pixels [N][3] <-> pairs [N/2][3]
+template <int N>
+__device__ __forceinline__ void to_pairs(const float (&x)[N][3], f2 (&p)[N / 2][3]) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p[i][c] = make_float2(x[2 * i][c], x[2 * i + 1][c]);
+}
+template <int N>
+__device__ __forceinline__ void from_pairs(const f2 (&p)[N / 2][3], float (&x)[N][3]) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            x[2 * i][c] = p[i][c].x;
+            x[2 * i + 1][c] = p[i][c].y;
+        }
+}
+
+// rgb2labw_group on pairs (N even)
+template <int N, int FMA_SEEDS>
+__device__ __forceinline__ void rgb2labw_pairs(const float (&rgb)[N][3], float (&w)[N][3]) {
+    constexpr int P = N / 2;
+    f2 v[P][3], l[P][3], f[P][3], o[P][3];
+    to_pairs<N>(rgb, v);
+    decode_pairs<P, true>(v, l);
+    xyzf_pairs<P, FMA_SEEDS, false>(l, f);
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        o[i][0] = add2(f[i][1], splat(-CT_LAB_W0_SHIFT));
+        o[i][1] = add2(f[i][0], neg2(f[i][1]));
+        o[i][2] = add2(f[i][1], neg2(f[i][2]));
+    }
+    from_pairs<N>(o, w);
+}
+
+// reinhard_group_h on pairs (N even)
+template <int N, int FMA_SEEDS>
+__device__ __forceinline__ void reinhard_pairs_h(const ReinhardFold &k, const float (&vin)[N][3], float (&out)[N][3]) {
+    constexpr int P = N / 2;
+    f2 v[P][3], l[P][3], f[P][3], g[P][3], x[P][3], c[P][3], o[P][3];
+    to_pairs<N>(vin, v);
+    decode_pairs<P, false>(v, l);
+    xyzf_pairs<P, FMA_SEEDS, true>(l, f);
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const f2 gy = fma2(splat(k.sL), f[i][1], splat(k.cL));
+        f2 gz = add2(gy, neg2(fma2(splat(k.sb), add2(f[i][1], neg2(f[i][2])), splat(k.cb))));
+        asm("max.NaN.f32 %0, %0, 0f00000000;" : "+f"(gz.x));  // skimage zeroes invalid z (and warns)
+        asm("max.NaN.f32 %0, %0, 0f00000000;" : "+f"(gz.y));
+        g[i][0] = add2(fma2(splat(k.sa), add2(f[i][0], neg2(f[i][1])), splat(k.ca)), gy);
+        g[i][1] = gy;
+        g[i][2] = gz;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) x[i][j] = mul2(mul2(g[i][j], g[i][j]), g[i][j]);
+    }
+    if (min_of2<P>(g) <= CT_THR_FINV_F) {
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                x[i][j] = select_gt(g[i][j], CT_THR_FINV_F, x[i][j], fma2(g[i][j], splat(1.0f / 7.787f), splat(-(16.0f / 116.0f) / 7.787f)));
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const f2 X = x[i][0], Y = x[i][1], Z = x[i][2];
+        c[i][0] = fma2(splat(-0.5428213080224701f), Z, fma2(splat(-1.5371515162713183f), Y, mul2(splat(3.079980302271805f), X)));
+        c[i][1] = fma2(splat(0.045247339514465995f), Z, fma2(splat(1.8759900014898907f), Y, mul2(splat(-0.9212477523232383f), X)));
+        c[i][2] = fma2(splat(1.1512320119619401f), Z, fma2(splat(-0.20404133836651123f), Y, mul2(splat(0.05289046109881184f), X)));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o[i][j] = fma2(splat(1.055f), ex2_2(mul2(splat(0.41666666f), lg2_2(c[i][j]))), splat(-0.055f));
+    }
+    if (min_of2<P>(c) <= CT_THR_ENC_F) {
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) o[i][j] = select_gt(c[i][j], CT_THR_ENC_F, o[i][j], mul2(splat(12.92f), c[i][j]));
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o[i][j] = make_float2(clip01_nan(o[i][j].x), clip01_nan(o[i][j].y));
+    from_pairs<N>(o, out);
+}
+
 }  // namespace lab
 }  // namespace ct

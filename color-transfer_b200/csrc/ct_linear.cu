@@ -29,6 +29,9 @@ struct MomentsArgs {
 
 // Cube-root seeds of the Lab kernels taken from the FMA pipe instead of MUFU (0..3 of the three
 // per pixel): with 0 both kernels are bound by the XU pipe, with 3 by instruction issue.
+#ifndef CT_LAB_PACKED   // 1: the fp32 Lab chain on pixel pairs (FFMA2), 0: the scalar chain (A/B, identical results)
+#define CT_LAB_PACKED 1
+#endif
 #ifndef CT_STATS_FMA_SEEDS
 #define CT_STATS_FMA_SEEDS 2
 #endif
@@ -74,7 +77,8 @@ template <int N>
 __device__ __forceinline__ void accumulate_lab(const float (&rgbf)[N][3], double (&acc)[9]) {
     float s[3] = {0.0f, 0.0f, 0.0f}, q[3] = {0.0f, 0.0f, 0.0f};
     float w[N][3];  // (L - 50) / 116, a / 500, b / 200: scaled back when the sums are combined
-    lab::rgb2labw_group<N, CT_STATS_FMA_SEEDS>(rgbf, w);
+    if constexpr (N % 2 == 0 && CT_LAB_PACKED) lab::rgb2labw_pairs<N, CT_STATS_FMA_SEEDS>(rgbf, w);
+    else lab::rgb2labw_group<N, CT_STATS_FMA_SEEDS>(rgbf, w);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
 #pragma unroll
@@ -144,7 +148,9 @@ __device__ __forceinline__ void moments_image(const Img &im, int64_t pair, const
     }
 }
 
-template <bool LAB>
+// ANY_U8: the instantiation that also holds the uint8 variants (launched when an image is uint8), so that
+// the float paths keep their own register allocation
+template <bool LAB, bool ANY_U8>
 __global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_CTAS_PER_SM : 3) moments_kernel(MomentsArgs a) {
     const int z = blockIdx.z;
     const int64_t pair = blockIdx.y;
@@ -154,16 +160,20 @@ __global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_CTAS_PER_SM : 3) moment
 
     const Img im = a.img[z];
     const int sel = a.kind[z] * 2 + a.vec[z];
-    __shared__ double dec_d[256];
-    __shared__ float dec_f[256];
-    if (a.kind[z] >= 4) {   // uint8 image (block-uniform)
+    __shared__ double dec_d[ANY_U8 ? 256 : 1];
+    __shared__ float dec_f[ANY_U8 ? 256 : 1];
+    if (ANY_U8 && a.kind[z] >= 4) {   // uint8 image (block-uniform)
         fill_decode(dec_d, dec_f, a.u8_as_f32[z]);
         __syncthreads();
     }
     const Decode dec{dec_d, dec_f};
     switch (sel) {
 #define CT_CASE(ID, T, L, V) case ID: moments_image<PixelIO<T, L>, V, LAB>(im, pair, dec, acc); break;
-        CT_FOR_EACH_SRC(CT_CASE)
+        CT_FOR_EACH_FLOAT_SRC(CT_CASE)
+        default:
+            if constexpr (ANY_U8) {
+                switch (sel) { CT_FOR_EACH_U8_SRC(CT_CASE) }
+            }
 #undef CT_CASE
     }
 
@@ -304,7 +314,8 @@ __global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_APPLY_CTAS_PER_SM : CT_
             if (HYB) {
                 float xs[GS][3], ys[GS][3];
                 SIO::unpack_sub_f(raw, q, dec, xs);
-                lab::reinhard_group_h<GS, CT_REINHARD_FMA_SEEDS>(fold, xs, ys);
+                if constexpr (GS % 2 == 0 && CT_LAB_PACKED) lab::reinhard_pairs_h<GS, CT_REINHARD_FMA_SEEDS>(fold, xs, ys);
+                else lab::reinhard_group_h<GS, CT_REINHARD_FMA_SEEDS>(fold, xs, ys);
                 DIO::template store<VEC, GS>(dst, a.dst.plane_stride, SIO::sub_pixel0(g, q), ys, clamp);
             } else {
                 double x[GS][3], y[GS][3];
@@ -402,8 +413,15 @@ int launch_moments(ct_context *h, const ct_batch *a, const ct_batch *b, int lab,
     m.method = (b && xform) ? method : -1;
     m.xform = xform;
     m.status = status;
-    if (lab) moments_kernel<true><<<dim3(nblk, B, nimg), kThreads, 0, h->stream>>>(m);
-    else moments_kernel<false><<<dim3(nblk, B, nimg), kThreads, 0, h->stream>>>(m);
+    const bool any_u8 = a->dtype == CT_U8 || (b && b->dtype == CT_U8);
+    const dim3 grid(nblk, B, nimg);
+    if (lab) {
+        if (any_u8) moments_kernel<true, true><<<grid, kThreads, 0, h->stream>>>(m);
+        else moments_kernel<true, false><<<grid, kThreads, 0, h->stream>>>(m);
+    } else {
+        if (any_u8) moments_kernel<false, true><<<grid, kThreads, 0, h->stream>>>(m);
+        else moments_kernel<false, false><<<grid, kThreads, 0, h->stream>>>(m);
+    }
     h->launches++;
     CT_CUDA(h, cudaGetLastError());
     return CT_OK;
