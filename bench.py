@@ -385,11 +385,15 @@ def main():
     # ---- per-kernel times: CUDA events after every launch of the fused driver, on two extra steps of the
     # very loop timed above (ct_profile_*); reported per pass over the F resident frame pairs
     handle.profile(True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
     step()
     step()
+    p1.record()
     prof = handle.profile_read(16384)
     handle.profile(False)
     n_pass = 2 * P
+    profiled_ms_per_pass = p0.elapsed_time(p1) / n_pass
     kern_ms, kern_launches = {}, {}
     for name, ms in prof:
         kind = name.split("_")[0]
@@ -413,6 +417,7 @@ def main():
                 "traffic": None if bpp is None else bpp * npix * F,
                 "traffic_source": None if bpp is None else bpp_src + ": ncu dram bytes per pixel of the steady-state launches x pixels per launch",
                 "kernel_ms_per_pass": {k: round(v, 4) for k, v in kern_ms.items()},
+                "profiled_ms_per_pass": round(profiled_ms_per_pass, 4),   # the same two steps end to end: kernels + what lies between two passes
                 "kernel_frac": {k: round(kind_bytes[k] * npix * F / (v / 1e3) / 1e9 / peak, 4) for k, v in kern_ms.items() if kind_bytes.get(k)},
                 "timing": "CUDA events after every launch of the fused driver (ct_profile_*), two steps right after the timed region",
                 "step_algorithmic_GBps": step_gbps, "step_frac": step_gbps / peak}

@@ -16,6 +16,9 @@
 #ifndef CT_RANGES_CHUNK
 #define CT_RANGES_CHUNK 4   // rotations evaluated per pass over a static image (1, 2 or 4)
 #endif
+#ifndef CT_HIST_COPIES_LOG2
+#define CT_HIST_COPIES_LOG2 3   // lane-interleaved copies of the three histograms for bins <= 256
+#endif
 #ifndef CT_HIST_STAGES
 #define CT_HIST_STAGES 3
 #endif
@@ -672,6 +675,30 @@ struct HistShared {
     float dec_f[U8 ? 256 : 1];
 };
 
+// exact bin of one sample on axis j (the slow path of the screen below)
+template <typename Shared>
+__device__ __noinline__ int hist_exact_bin(const Shared &sh, int j, double x0, double x1, double x2, int bins) {
+    const double x[3] = {x0, x1, x2};
+    const double p = dot3(sh.rot + 3 * j, x);
+    return bin_exact(p, sh.grid[j].lo, sh.grid[j].inv, sh.grid[j].step, bins);
+}
+
+// CT_HIST_SCREEN: bin in packed fp32 first, exactly only where that cannot decide.
+//
+// The exact rule (np.histogram) needs p = rot_j . x in fp64 and a comparison with the fp64 edge: 9 fp64
+// instructions per sample and axis, which made K5 instruction / latency bound (round 1: 0.77 of the HBM
+// roofline, fp64 pipe 50 % busy).  But t = (p - lo) / (hi - lo) * bins only has to be known well enough to
+// say on which side of an integer it lies.  So t is evaluated in fp32 with the rotation row pre-scaled
+// (two axes per FFMA2), rounded to the nearest integer k' with the magic-number add, and the sample is
+// SAFE when |t - k'| > eps: the bin is then k' - (t < k').  eps bounds the fp32 error of t,
+//     |t32 - t| <= 2^-24 inv (5 S + 4 |lo|),  S = |x0| + |x1| + |x2|
+// (fl32 of the scaled row and offset, fl32 of the pixel, three fma roundings; the grid's own edges sit
+// within 1e-13 of the integers in t), evaluated per pixel.  Unsafe samples - about 1 in 1000 - take the
+// exact fp64 path above, so the counts stay bit-exact.
+#ifndef CT_HIST_SCREEN
+#define CT_HIST_SCREEN 1
+#endif
+
 template <typename IO, bool VEC, int CL2, typename Shared>  // CL2: log2(copies) when known at compile time, else -1
 __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Shared &sh,
                                            int bins, int copies_log2_rt, unsigned int *hist, HistPipe &pipe,
@@ -682,6 +709,103 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Sh
     constexpr int G = IO::G, GS = IO::GS;
     const Decode dec{sh.dec_d, sh.dec_f};
     const int copy = threadIdx.x & ((1 << copies_log2) - 1);
+    // this lane's copy of each axis histogram as a 32-bit shared-window address: the slot of bin k
+    // is one shift-add away (the generic-pointer form cost four integer instructions per sample)
+    uint32_t hb[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) hb[j] = smem_u32(hist) + 4u * (uint32_t)(((j * bins) << copies_log2) + copy);
+    auto count = [&](int j, int k) {
+        atomicAdd(reinterpret_cast<unsigned int *>(__cvta_shared_to_generic(hb[j] + ((uint32_t)k << (copies_log2 + 2)))), 1u);
+    };
+    int64_t p = (int64_t)first_block * kThreads + threadIdx.x, step = (int64_t)nblocks * kThreads;
+#if CT_HIST_SCREEN
+    // screen rows: (axis 0, axis 1) and (axis 2, unused)
+    float2 s0[2], s1[2], s2[2], sc[2];
+    float ea[3], eb[3];
+    {
+        float r[3][3], c[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double inv = sh.grid[j].inv, lo = sh.grid[j].lo;
+            const bool ok = inv > 0.0 && inv < 1e30 && fabs(lo) < 1e30;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) r[j][i] = ok ? (float)(sh.rot[3 * j + i] * inv) : 0.0f;
+            c[j] = ok ? (float)(-lo * inv) : 0.0f;                       // not ok: t = 0, every sample unsafe
+            ea[j] = ok ? (float)(inv * 3.7252902984619141e-07) : 0.0f;   // 6.25 * 2^-24 inv
+            eb[j] = ok ? (float)(inv * fabs(lo) * 2.9802322387695312e-07) + 1e-7f : 1.0f;   // 5 * 2^-24 inv |lo|
+        }
+        s0[0] = make_float2(r[0][0], r[1][0]); s1[0] = make_float2(r[0][1], r[1][1]); s2[0] = make_float2(r[0][2], r[1][2]);
+        s0[1] = make_float2(r[2][0], 0.0f); s1[1] = make_float2(r[2][1], 0.0f); s2[1] = make_float2(r[2][2], 0.0f);
+        sc[0] = make_float2(c[0], c[1]);
+        sc[1] = make_float2(c[2], 0.0f);
+    }
+    const unsigned last = (unsigned)(bins - 1);
+    const float2 magic = make_float2(12582912.0f, 12582912.0f);   // 1.5 * 2^23: adding it rounds to the nearest integer
+    // bins of one pixel on the three axes; false: some axis could not be decided in fp32
+    auto screen = [&](const float (&x)[3], int (&k)[3]) -> bool {
+        const float2 x0 = make_float2(x[0], x[0]), x1 = make_float2(x[1], x[1]), x2 = make_float2(x[2], x[2]);
+        const float sum = fabsf(x[0]) + fabsf(x[1]) + fabsf(x[2]);
+        bool safe = true;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float2 t = __ffma2_rn(s2[h], x2, __ffma2_rn(s1[h], x1, __ffma2_rn(s0[h], x0, sc[h])));
+            const float2 u = __fadd2_rn(t, magic);
+            const float2 fr = __fadd2_rn(t, make_float2(-(u.x - 12582912.0f), -(u.y - 12582912.0f)));
+            const float uu[2] = {u.x, u.y}, ff[2] = {fr.x, fr.y};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = 2 * h + e;
+                if (j < 3) {
+                    safe &= fabsf(ff[e]) > fmaf(sum, ea[j], eb[j]);     // false for NaN
+                    const int kk = (__float_as_int(uu[e]) - 0x4B400000) + (__float_as_int(ff[e]) >> 31);
+                    k[j] = (int)min((unsigned)kk, last);
+                }
+            }
+        }
+        return safe;
+    };
+    if (VEC) {
+        const int ntiles = (int)(im.npix / (kThreads * G));
+        pipe_for_each_group<IO>(pipe, base, im.plane_stride, ntiles, first_block, nblocks, zero,
+                                [&](const typename IO::Raw &raw, int64_t) {
+#pragma unroll
+                                    for (int q = 0; q < IO::NSUB; ++q) {
+                                        float xf[GS][3];
+                                        IO::unpack_sub_f(raw, q, dec, xf);
+                                        int k[GS][3];
+                                        bool safe[GS], all = true;
+#pragma unroll
+                                        for (int i = 0; i < GS; ++i) {
+                                            safe[i] = screen(xf[i], k[i]);
+                                            all &= safe[i];
+                                        }
+                                        if (!all) {
+                                            double x[GS][3];
+                                            IO::unpack_sub(raw, q, dec, x);
+#pragma unroll
+                                            for (int i = 0; i < GS; ++i)
+                                                if (!safe[i]) {
+#pragma unroll
+                                                    for (int j = 0; j < 3; ++j) k[i][j] = hist_exact_bin(sh, j, x[i][0], x[i][1], x[i][2], bins);
+                                                }
+                                        }
+#pragma unroll
+                                        for (int i = 0; i < GS; ++i)
+#pragma unroll
+                                            for (int j = 0; j < 3; ++j) count(j, k[i][j]);
+                                    }
+                                });
+        p = (int64_t)ntiles * kThreads * G + threadIdx.x;   // the tail belongs to block 0
+        step = kThreads;
+        if (first_block != 0) return;
+    }
+    for (; p < im.npix; p += step) {
+        double x[3];
+        IO::load1(base, im.plane_stride, p, dec, x);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) count(j, hist_exact_bin(sh, j, x[0], x[1], x[2], bins));
+    }
+#else
     double r[9], lo[3], inv[3], stp[3];
 #pragma unroll
     for (int i = 0; i < 9; ++i) r[i] = sh.rot[i];
@@ -691,20 +815,10 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Sh
         inv[j] = sh.grid[j].inv;
         stp[j] = sh.grid[j].step;
     }
-    // this lane's copy of each axis histogram as a 32-bit shared-window address: the slot of bin k
-    // is one shift-add away (the generic-pointer form cost four integer instructions per sample)
-    uint32_t hb[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) hb[j] = smem_u32(hist) + 4u * (uint32_t)(((j * bins) << copies_log2) + copy);
     auto one = [&](const double(&x)[3]) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const double p = dot3(r + 3 * j, x);
-            const int k = bin_exact(p, lo[j], inv[j], stp[j], bins);
-            atomicAdd(reinterpret_cast<unsigned int *>(__cvta_shared_to_generic(hb[j] + ((uint32_t)k << (copies_log2 + 2)))), 1u);
-        }
+        for (int j = 0; j < 3; ++j) count(j, bin_exact(dot3(r + 3 * j, x), lo[j], inv[j], stp[j], bins));
     };
-    int64_t p = (int64_t)first_block * kThreads + threadIdx.x, step = (int64_t)nblocks * kThreads;
     if (VEC) {
         const int ntiles = (int)(im.npix / (kThreads * G));
         pipe_for_each_group<IO>(pipe, base, im.plane_stride, ntiles, first_block, nblocks, zero,
@@ -726,12 +840,16 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Sh
         IO::load1(base, im.plane_stride, p, dec, x);
         one(x);
     }
+#endif
 }
 
 // ANY_U8: the instantiation that also holds the uint8 variants (launched when either image is uint8);
 // float / double images run the instantiation without them.
 template <bool ANY_U8>
-__global__ void __launch_bounds__(kThreads, 3) hist_kernel(HistArgs a) {
+#ifndef CT_HIST_MINB
+#define CT_HIST_MINB 3
+#endif
+__global__ void __launch_bounds__(kThreads, CT_HIST_MINB) hist_kernel(HistArgs a) {
     // tile pipeline (stages, then one barrier set per image) | histograms; the front is later
     // reused by the LUT build
     extern __shared__ __align__(16) double sm_dyn[];
@@ -760,9 +878,9 @@ __global__ void __launch_bounds__(kThreads, 3) hist_kernel(HistArgs a) {
         const int sel = a.kind[z] * 2 + a.vec[z];
 #define CT_HIST_CALL(T, L, V, CL2V) \
     hist_image<PixelIO<T, L>, V, CL2V>(a.img[z], pair, sh, bins, a.copies_log2, hist, pipe, blockIdx.x, gridDim.x, a.zero)
-#define CT_CASE_3(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, 3); break;
+#define CT_CASE_3(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, CT_HIST_COPIES_LOG2); break;
 #define CT_CASE_g(ID, T, L, V) case ID: CT_HIST_CALL(T, L, V, -1); break;
-        if (a.copies_log2 == 3) {  // bins <= 256: the default 255
+        if (a.copies_log2 == CT_HIST_COPIES_LOG2) {  // bins <= 256: the default 255
             switch (sel) {
                 CT_FOR_EACH_FLOAT_SRC(CT_CASE_3)
                 default:
@@ -1117,7 +1235,7 @@ static LutArgs lut_args(const ct_idt_stage *s, int keep_counts, const ct_idt_tra
     return l;
 }
 
-static int copies_log2_for(int bins) { return bins <= 256 ? 3 : (bins <= 512 ? 2 : 0); }
+static int copies_log2_for(int bins) { return bins <= 256 ? CT_HIST_COPIES_LOG2 : (bins <= 512 ? (CT_HIST_COPIES_LOG2 < 2 ? CT_HIST_COPIES_LOG2 : 2) : 0); }
 
 int launch_hist(ct_context *h, const ct_idt_stage *s, int fuse_lut, const ct_idt_trace *trace,
                 int trace_iter, int trace_niter) {
