@@ -72,6 +72,8 @@ SIGNATURES = {
                                                   ctypes.c_int32]),
     "ct_idt_transfer_host_u8": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
                                                _P, ctypes.c_int32, ctypes.c_int32]),
+    "ct_linear_stats_host": (ctypes.c_int, [_P, ctypes.c_int, _BP, _BP, _P, _P]),
+    "ct_linear_apply_staged_host": (ctypes.c_int, [_P, ctypes.c_int, _P, _BP]),
     "ct_profile_enable": (ctypes.c_int, [_P, ctypes.c_int]),
     "ct_profile_read": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32]),
     "ct_idt_key_of": (ctypes.c_int64, [ctypes.c_double]),

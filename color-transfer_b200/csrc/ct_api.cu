@@ -616,6 +616,49 @@ int ct_linear_transfer_host(ct_handle h, int method, const ct_batch *target, con
     return first_bad_status(h, h->status, target->count);
 }
 
+int ct_linear_stats_host(ct_handle h, int lab, const ct_batch *target, const ct_batch *reference, double *sums_t,
+                         double *sums_r) {
+    CT_ENTER(h);
+    h->staged_valid = false;
+    CT_TRY(check_batch(h, target, "target"));
+    CT_TRY(check_batch(h, reference, "reference"));
+    if (!sums_t || !sums_r) return fail(h, CT_E_INVALID, "sums is NULL");
+    if (target->count != 1 || reference->count != 1) return fail(h, CT_E_UNSUPPORTED, "the two-phase transfer takes one pair per call");
+    CT_TRY(ensure_scratch(h, 1));
+    const size_t tb = align_up(image_bytes(target)), rb = align_up(image_bytes(reference));
+    const size_t ob = align_up(sizeof(double) * 3 * (size_t)target->npix);   // room for a float64 result
+    CT_TRY(ensure_stage(h, tb + rb + ob));
+    unsigned char *base = static_cast<unsigned char *>(h->stage);
+    CT_CUDA(h, cudaMemcpyAsync(base, target->data, image_bytes(target), cudaMemcpyHostToDevice, h->stream));
+    CT_CUDA(h, cudaMemcpyAsync(base + tb, reference->data, image_bytes(reference), cudaMemcpyHostToDevice, h->stream));
+    const ct_batch t1 = single(target, base), r1 = single(reference, base + tb);
+    CT_TRY(launch_moments(h, &t1, &r1, lab, h->sums, -1, nullptr, nullptr));
+    CT_CUDA(h, cudaMemcpyAsync(sums_t, h->sums, sizeof(double) * CT_MOMENT_DOUBLES, cudaMemcpyDeviceToHost, h->stream));
+    CT_CUDA(h, cudaMemcpyAsync(sums_r, h->sums + CT_MOMENT_DOUBLES, sizeof(double) * CT_MOMENT_DOUBLES, cudaMemcpyDeviceToHost, h->stream));
+    CT_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->staged_target = t1;
+    h->staged_out = base + tb + rb;
+    h->staged_valid = true;
+    return CT_OK;
+}
+
+int ct_linear_apply_staged_host(ct_handle h, int method, const double *xform, const ct_batch *out) {
+    CT_ENTER(h);
+    if (method < CT_REINHARD || method > CT_MKL_CHOLESKY) return fail(h, CT_E_INVALID, "unknown method %d", method);
+    if (!h->staged_valid) return fail(h, CT_E_INVALID, "no staged pair: call ct_linear_stats_host first");
+    h->staged_valid = false;
+    CT_TRY(check_batch(h, out, "out"));
+    if (!xform) return fail(h, CT_E_INVALID, "xform is NULL");
+    if (out->count != 1 || out->npix != h->staged_target.npix || out->layout != CT_HWC)
+        return fail(h, CT_E_INVALID, "out must be one CT_HWC image of the staged target's size");
+    CT_CUDA(h, cudaMemcpyAsync(h->xform, xform, sizeof(double) * CT_XFORM_DOUBLES, cudaMemcpyHostToDevice, h->stream));
+    const ct_batch o1 = single(out, h->staged_out);
+    CT_TRY(launch_apply(h, method, &h->staged_target, h->xform, &o1));
+    CT_CUDA(h, cudaMemcpyAsync(out->data, h->staged_out, image_bytes(out), cudaMemcpyDeviceToHost, h->stream));
+    CT_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CT_OK;
+}
+
 int ct_linear_transfer_host_u8(ct_handle h, int method, const uint8_t *target, const uint8_t *reference, uint8_t *out,
                                int32_t count, int64_t npix_target, int64_t npix_reference, int32_t as_float32) {
     CT_ENTER(h);

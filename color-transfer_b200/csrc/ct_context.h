@@ -39,6 +39,11 @@ struct ct_context {
     std::vector<int> prof_id;
     size_t prof_n = 0;
 
+    // ct_linear_stats_host -> ct_linear_apply_staged_host: the target staged on the device, where its result goes
+    ct_batch staged_target = {};
+    void *staged_out = nullptr;
+    bool staged_valid = false;
+
     double *u8_tmp = nullptr;   // inside ws: float64 result of a one-iteration IDT on uint8 frames before it is encoded
 
     // K4 screen: pixels with |x0|+|x1|+|x2| above this take the exact fp64 path (CT_RANGES_BOUND)

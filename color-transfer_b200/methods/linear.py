@@ -84,13 +84,53 @@ def color_transfer_between_images(target, reference, *, out=None, handle=None):
     return _run(_cabi.CT_REINHARD, t, r, out_dtype, out, handle)
 
 
-def color_transfer_in_correlated_color_space(target, reference, *, out=None, handle=None):
+def _mean_cov(sums):
+    """np.mean(axis=0) and np.cov(X.T) (ddof 1) from the device's raw moments about 0.5
+    {n, S(x-K), S(x-K)(x-K)^T as 00,01,02,11,12,22} (ref: methods/linear.py:64-67)."""
+    n = sums[0]
+    m1 = sums[1:4] / n
+    sxx = np.array([[sums[4], sums[5], sums[6]], [sums[5], sums[7], sums[8]], [sums[6], sums[8], sums[9]]])
+    return m1 + 0.5, (sxx - n * np.outer(m1, m1)) / (n - 1)
+
+
+def color_transfer_in_correlated_color_space(target, reference, *, out=None, handle=None, lapack_signs=True):
     """Color Transfer in Correlated Color Space (Xiao & Ma, 2006) - ref: methods/linear.py:45-82.
 
-    Returns float64, not clipped.  The singular-vector signs that LAPACK leaves arbitrary are
-    fixed by orienting each reference axis along its target axis.
+    Returns float64, not clipped.  The transform depends on the signs LAPACK happens to give the
+    singular vectors of the two 3x3 covariances, which no device-side convention can predict (on random
+    covariance pairs the natural rule "orient u_r along u_t" disagrees in more than half the cases).
+    The drop-in therefore brings the covariances (reduced on the device) back to the host, runs the
+    reference's own three lines on them - np.linalg.svd, i.e. dgesdd (linear.py:69-78) - and applies
+    the resulting matrix on the device.  ``lapack_signs=False`` keeps everything on the device with the
+    orientation rule (what the batched / device-resident entry points do).
     """
-    return _run(_cabi.CT_CCS, target, reference, np.float64, out, handle)
+    if not lapack_signs:
+        return _run(_cabi.CT_CCS, target, reference, np.float64, out, handle)
+    t = _as_image(target, "target")
+    r = _as_image(reference, "reference")
+    h = handle or _cabi.default_handle()
+    tb, t_keep = _cabi.batch_from_numpy(t)
+    rb, r_keep = _cabi.batch_from_numpy(r)
+    if out is None:
+        out = np.empty(t.shape, dtype=np.float64)
+    elif out.shape != t.shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous float64 array of the target's shape")
+    ob, _ = _cabi.batch_from_numpy(out)
+    sums_t, sums_r = np.empty(_cabi.CT_MOMENT_DOUBLES), np.empty(_cabi.CT_MOMENT_DOUBLES)
+    h.check(h.lib.ct_linear_stats_host(h.h, 0, tb, rb, sums_t.ctypes.data, sums_r.ctypes.data))
+    mean_t, cov_t = _mean_cov(sums_t)
+    mean_r, cov_r = _mean_cov(sums_r)
+    with np.errstate(divide="ignore", invalid="ignore"):      # a singular covariance propagates inf / NaN like the reference
+        u_t, s_t, _ = np.linalg.svd(cov_t)                    # linear.py:69
+        u_r, s_r, _ = np.linalg.svd(cov_r)                    # linear.py:70
+        transform = u_t @ np.diag(1 / np.sqrt(s_t)) @ np.diag(np.sqrt(s_r)) @ np.linalg.inv(u_r)   # linear.py:72-78
+    xform = np.zeros(_cabi.CT_XFORM_DOUBLES)
+    xform[:9] = transform.T.reshape(-1)       # out = (x - mean_t) @ M + mean_r with M = T.T (linear.py:80)
+    xform[9:12] = mean_t
+    xform[12:15] = mean_r
+    h.check(h.lib.ct_linear_apply_staged_host(h.h, _cabi.CT_CCS, xform.ctypes.data, ob))
+    del t_keep, r_keep
+    return out
 
 
 def monge_kantorovitch_color_transfer(target, reference, decomposition="MK", *, out=None, handle=None):

@@ -130,6 +130,17 @@ int ct_linear_transfer(ct_handle h, int method, const ct_batch *target,
 int ct_linear_transfer_host(ct_handle h, int method, const ct_batch *target,
                             const ct_batch *reference, const ct_batch *out);
 
+/* Two-phase host transfer of ONE pair: the statistics come back to the host between the two device passes so
+ * that the caller can do the 3x3 algebra itself.  The Python wrapper of color_transfer_in_correlated_color_space
+ * uses it to run numpy's SVD (LAPACK dgesdd, the reference's own call at linear.py:69-70) on the two
+ * covariances and so reproduce the singular-vector SIGNS the reference gets, which no convention can predict.
+ * ct_linear_stats_host copies both images to the device (they stay staged inside the handle until its next
+ * host call) and returns their raw moments; ct_linear_apply_staged_host applies `xform` (host, CT_XFORM_DOUBLES,
+ * layout of ct_linear_solve) to the staged target and copies the result to `out` (host). */
+int ct_linear_stats_host(ct_handle h, int lab, const ct_batch *target, const ct_batch *reference,
+                         double *sums_t /* host [10] */, double *sums_r /* host [10] */);
+int ct_linear_apply_staged_host(ct_handle h, int method, const double *xform, const ct_batch *out);
+
 /* ------------------------------------------------------------------ IDT (iterative.py:8-59) */
 #define CT_IDT_MAX_BINS 1024
 #define CT_IDT_KEYS 6 /* per pair and iteration: monotone int64 keys of lo[3], -hi[3] */

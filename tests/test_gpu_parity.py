@@ -46,16 +46,42 @@ def test_mkl_and_ccs(api, h, w, ref_shape, dtype):
         assert out.dtype == np.float64
         err, _ = _close(out, oracle.monge_kantorovitch_color_transfer(t64, r64, dec))
         assert err < 1e-9
+    # Xiao CCS: the drop-in takes LAPACK's singular-vector signs from numpy's SVD of the device-reduced
+    # covariances (the reference's own call), so it must match the reference whatever those signs are
     out = lin.color_transfer_in_correlated_color_space(t, r)
     ref = oracle.color_transfer_in_correlated_color_space(t64, r64)
+    assert out.dtype == np.float64
+    scale = max(1.0, float(np.max(np.abs(ref))))
+    assert float(np.max(np.abs(out - ref))) <= 1e-8 * scale, "CCS (LAPACK signs) differs from the reference"
+    # the all-device variant orients u_r along u_t: the reference's answer or one of its 8 sign choices
+    out = lin.color_transfer_in_correlated_color_space(t, r, lapack_signs=False)
     err = float(np.max(np.abs(out - ref)))
-    if err > TOL:  # LAPACK's free singular-vector signs: compare after aligning them
+    if err > TOL:
         mu_t, cov_t = oracle.mean_and_cov(t64)
         mu_r, cov_r = oracle.mean_and_cov(r64)
         best = min(
             float(np.max(np.abs(out - ((t64.reshape(-1, 3) - mu_t) @ oracle.ccs_matrix(cov_t, cov_r, s).T + mu_r).reshape(t.shape))))
             for s in [(a, b, c) for a in (1, -1) for b in (1, -1) for c in (1, -1)])
-        assert best <= 1e-8, f"CCS differs from every sign choice: {best:.3e}"
+        assert best <= 1e-8 * scale, f"CCS differs from every sign choice: {best:.3e}"
+
+
+def test_ccs_random_pairs_match_lapack_signs(api):
+    """40 random image pairs with unrelated colour statistics (where the device's orientation rule often
+    disagrees with LAPACK): the drop-in function must still equal the reference."""
+    lin, _, oracle = api
+    rng = np.random.default_rng(11)
+    needed = 0
+    for i in range(40):
+        a = rng.standard_normal((3, 3)) * 0.15
+        b = rng.standard_normal((3, 3)) * 0.15
+        t = np.clip(0.5 + rng.standard_normal((40, 50, 3)) @ a.T, 0, 1)
+        r = np.clip(0.5 + rng.standard_normal((37, 45, 3)) @ b.T, 0, 1)
+        ref = oracle.color_transfer_in_correlated_color_space(t, r)
+        out = lin.color_transfer_in_correlated_color_space(t, r)
+        assert float(np.max(np.abs(out - ref))) <= 1e-8 * max(1.0, float(np.max(np.abs(ref)))), f"pair {i}"
+        dev = lin.color_transfer_in_correlated_color_space(t, r, lapack_signs=False)
+        needed += float(np.max(np.abs(dev - ref))) > 1e-6
+    print(f"\n[ccs] the all-device orientation rule differs from LAPACK on {needed} of 40 random pairs; the drop-in on none")
 
 
 @pytest.mark.parametrize("h,w,ref_shape", PAIRS)

@@ -28,3 +28,17 @@ metrics.icid(x, y); metrics.icid(x, y, downsampling=False, omit_maps67=True); me
 big = torch.rand(1, 3, 530, 300, device="cuda"); metrics.icid(big, big.flip(3)); metrics.ssim(big, big.flip(3))
 torch.cuda.synchronize()
 print("sanitizer workload done")
+# round 2: uint8 frames decoded / encoded inside the kernels (interleaved and planar, float32 / uint8 / clamped results),
+# the seeded fp32 screens of K4 / K5 (6 rotations = two K4 chunks), the split-rotation K4 variant, scalar tails
+t8d = torch.from_numpy(t8).cuda(); r8d = torch.from_numpy(r8).cuda()
+rot6 = torch.from_numpy(np.stack([batch.draw_rotations(6) for _ in range(2)])).cuda()
+device.idt_transfer(t8d, r8d, rot6, 255, 6)
+device.idt_transfer(t8d, r8d, rot6[:, :4].contiguous(), 255, 4, out_dtype=torch.float32, clamp=True)
+t8p = t8d.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+device.idt_transfer(t8p, r8d, rot6[:, :2].contiguous(), 64, 2, as_float32=False)
+for code in (_cabi.CT_REINHARD, _cabi.CT_MKL_MK):
+    device.linear_transfer(code, t8p, r8d); device.linear_transfer(code, t8d, r8d, out_dtype=torch.float32, clamp=True)
+odd = torch.rand(3, 33, 37, 3, device="cuda", dtype=torch.float64)
+device.idt_transfer(odd, odd.flip(0), rot6[:1, :4].expand(3, 4, 3, 3).contiguous(), 255, 4)
+torch.cuda.synchronize()
+print("round-2 sanitizer workload done")
