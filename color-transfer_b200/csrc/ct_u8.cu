@@ -4,8 +4,9 @@
 //        ref: utils/data.py:106) or float64 (skimage.img_as_float, ref: utils/postprocess.py:138)
 //   out: np.rint(np.clip(y, 0, 1) * 255).astype(uint8)  (img_as_ubyte of the clipped result,
 //        ref: utils/postprocess.py:138; Runner clamps the same way, ref: methods/__init__.py:30)
-// These are separate streaming kernels (one extra pass each); fusing them into K3 / K7 is left
-// for a later round.
+// Since round 2 the transfer kernels decode and encode uint8 images themselves (PixelIO<uint8_t, .>,
+// ct_common.cuh); these streaming conversions remain for the one case without a float64 state to
+// convert from (a one-iteration IDT on uint8 frames through the host API).
 #include "ct_context.h"
 
 namespace ct {

@@ -171,11 +171,13 @@ typedef struct ct_idt_stage {
 int64_t ct_idt_key_of(double value);
 double ct_idt_value_of(int64_t key);
 
-/* Set n keys to "+inf" so that atomic minima can be folded in. */
+/* Set n keys to "+inf" so that atomic minima can be folded in (the fused driver lets K4a do it). */
 int ct_idt_keys_init(ct_handle h, int64_t *keys, int64_t n);
 /* K4: fold min(p), min(-p) of the projections p = rot_k @ x (iterative.py:34-35, 39-40) of every
  * pixel of `images` into keys, for n_rot consecutive rotations k (rot + 9k -> keys + 6k) in one
- * pass over the image.  The target needs n_rot = 1 (iteration 0); the reference never changes,
+ * pass over the image (per 4 rotations: K4a seeds exact extremes from a subsample, K4b screens every
+ * pixel in packed fp32 and evaluates the exact fp64 projections only where needed - the result is
+ * the exact fp64 minimum / maximum).  The target needs n_rot = 1 (iteration 0); the reference never changes,
  * so its range under all n_iter rotations is taken up front. */
 int ct_idt_ranges(ct_handle h, const ct_batch *images, const double *rot, int64_t rot_stride,
                   int32_t n_rot, int64_t *keys, int64_t keys_stride, int32_t *status);
@@ -201,10 +203,12 @@ typedef struct ct_idt_trace {
 } ct_idt_trace;
 
 size_t ct_idt_workspace_bytes(int64_t npix_target, int32_t count, int32_t bins, int32_t n_iter);
-/* Whole IDT: 3 + 2*n_iter launches (n_iter <= 4).  rotations: dev [B][n_iter][9], drawn by the caller (the
+/* Whole IDT: 3 + 2*n_iter launches for n_iter <= 4 (one more K4 pair per further 4 rotations of the reference's
+ * up-front pass).  rotations: dev [B][n_iter][9], drawn by the caller (the
  * Python wrapper calls scipy.stats.special_ortho_group.rvs once per iteration, in order, so the
- * global numpy RNG advances exactly as at iterative.py:32).  `out` must be float64 CT_HWC.
- * workspace may be NULL (the handle then grows its own). */
+ * global numpy RNG advances exactly as at iterative.py:32).  `out`: float64 CT_HWC (the reference's result), or - written
+ * by the last iteration's kernel, n_iter >= 2 - uint8 (clip + round) / float32 CT_HWC (optional CT_BATCH_CLAMP01).
+ * target / reference may be CT_U8 frames.  workspace may be NULL (the handle then grows its own). */
 int ct_idt_transfer(ct_handle h, const ct_batch *target, const ct_batch *reference,
                     const ct_batch *out, const double *rotations, int32_t bins, int32_t n_iter,
                     void *workspace, size_t workspace_bytes, const ct_idt_trace *trace,
@@ -226,7 +230,7 @@ int ct_acg_transfer_host(ct_handle h, const ct_batch *target, const ct_batch *re
 
 /* ------------------------------------------------------------------ uint8 frames
  * Stacks of `count` interleaved uint8 [npix,3] frames in host memory; 3 bytes per pixel cross
- * PCIe in each direction.  Frames are decoded exactly as the reference's loaders do
+ * PCIe in each direction and the kernels decode / encode them as they read / write (CT_U8 batches).  Frames are decoded exactly as the reference's loaders do
  * (as_float32 != 0: float32 k/255, ref utils/data.py:106; else float64 k/255.0 as
  * skimage.img_as_float, ref utils/postprocess.py:138), transferred with the kernels above, and the
  * result is clipped to [0,1] and rounded to uint8 (np.rint, i.e. img_as_ubyte of the clipped

@@ -183,7 +183,7 @@ def test_uint8_frame_io(mods, as_float32):
         out = batch.linear_transfer_frames_u8(name, t8, r8, as_float32=as_float32)
         for i in range(B):
             want = quantise(fn(tf[i].astype(np.float64), rf[i].astype(np.float64)))
-            assert np.mean(out[i] == want) >= 0.999
+            assert np.mean(out[i] == want) >= (0.999 if H * W < 5000 else 0.9999)   # 37 x 45 frames: one flip is 2e-4
     # the float path on the decoded frames gives the same bytes
     again = quantise(batch.idt_frames(tf, rf, rotations=rot))
     assert np.array_equal(again, batch.idt_frames_u8(t8, r8, rotations=rot, as_float32=as_float32))

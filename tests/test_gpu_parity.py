@@ -123,7 +123,9 @@ def test_inputs_not_modified_and_runner_layout(api):
     out = lin.monge_kantorovitch_color_transfer(tv, rv)
     _close(out, oracle.monge_kantorovitch_color_transfer(t.astype(np.float64), r.astype(np.float64)))
     out = lin.color_transfer_between_images(tv, rv)
-    _close(out, oracle.color_transfer_between_images(t.astype(np.float64), r.astype(np.float64)), u8=0.999)
+    # (one flipped value of a < 5 000-pixel image is 2e-4: the 99.99 % gate applies from that size up)
+    _close(out, oracle.color_transfer_between_images(t.astype(np.float64), r.astype(np.float64)),
+           u8=0.999 if t.shape[0] * t.shape[1] < 5000 else U8_MIN)
     np.random.seed(3)
     out = it.iterative_distribution_transfer(tv, rv)
     np.random.seed(3)
@@ -291,7 +293,7 @@ def test_automated_color_grading(api, h, w, dtype):
         # float64 oracle like the linear functions
         np.random.seed(13)
         out = it.automated_color_grading(t, r)
-        _close(out, want, u8=0.999)
+        _close(out, want, u8=0.999 if h * w < 5000 else U8_MIN)
 
 
 def test_automated_color_grading_pair0964(api, pair0964, golden):
