@@ -953,9 +953,25 @@ struct RemapShared {
     double rot[18];
     AxisGrid grid[3];
     double red[kWarps][6];
+    unsigned amb[3];
     double dec_d[U8 ? 256 : 1];
     float dec_f[U8 ? 256 : 1];
 };
+
+// K7 takes the bin of a sample as floor(t~), t~ = (p - lo) * inv rounded to 2^-20, whenever t~ is not within
+// 2^-20 of an integer.  That equals the searchsorted answer against the tabulated edges if the distance between
+// t~ and the position of every edge in t-space is below 2^-20: |t~ - t| <= 3 * 2^-53 * bins + 2^-21 (p - lo, inv
+// and the final rounding) and |edges[k] - (lo + k (hi - lo) / bins)| <= 2^-51 * max(|lo|, |hi|), i.e.
+// 2^-51 * max(|lo|, |hi|) * inv in t-space.  True for every grid whose width is not below ~1e-9 of its magnitude.
+#ifndef CT_REMAP_FLOOR
+#define CT_REMAP_FLOOR 1
+#endif
+constexpr int kFracBits = 20;
+constexpr double kMagicFrac = 6442450944.0;   // 1.5 * 2^32: ulp 2^-20
+__device__ __forceinline__ unsigned remap_ambiguity(const AxisGrid &g, int bins) {
+    const double slack = 3.0 * 1.1102230246251565e-16 * bins + 4.440892098500626e-16 * fmax(fabs(g.lo), fabs(g.hi)) * g.inv;
+    return slack < 2.3841857910156250e-07 /* 2^-22 */ ? 3u : (1u << kFracBits);
+}
 
 template <typename SIO, typename DIO, bool VEC, bool NEXT, bool ROUND32>
 __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, const RemapShared<SIO::kU8> &sh,
@@ -975,10 +991,12 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
         r[i] = sh.rot[i];
         rn[i] = NEXT ? sh.rot[9 + i] : 0.0;
     }
+    unsigned amb[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         lo[j] = sh.grid[j].lo;
         inv[j] = sh.grid[j].inv;
+        amb[j] = sh.amb[j];
     }
     auto one = [&](const double(&x)[3], double(&y)[3]) {
         double d[3];
@@ -987,9 +1005,23 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
             const double p = dot3(r + 3 * j, x);
             const double *edges = tab + j * E;
             const double2 *ent = reinterpret_cast<const double2 *>(tab + (3 + 2 * j) * E);
+#if CT_REMAP_FLOOR
+            // floor((p - lo) * inv) straight from a fixed-point magic number (20 fractional bits in the low
+            // mantissa word); only a sample within 2^-20 of a grid line - where the estimate and the exact
+            // edge could disagree - goes through the comparison against the tabulated edge.  amb[j] is 3,
+            // or 2^20 ("always compare") on a grid too narrow for its magnitude (remap_kernel prologue).
+            const unsigned w = (unsigned)__double2loint(fma(p - lo[j], inv[j], kMagicFrac));
+            int k = (int)(w >> kFracBits);
+            if (((w + 1u) & ((1u << kFracBits) - 1u)) < amb[j]) {
+                const int ke = bin_estimate(p, lo[j], inv[j], bins);
+                k = ke - (p < edges[ke] ? 1 : 0);
+            }
+            k = (int)min((unsigned)k, (unsigned)bins);
+#else
             const int ke = bin_estimate(p, lo[j], inv[j], bins);
             // bin index BEFORE folding p == hi into the last bin: ke - (p < edges[ke]) in [0, bins]
             const int k = (int)min((unsigned)(ke - (p < edges[ke] ? 1 : 0)), (unsigned)bins);
+#endif
             const double xp = edges[k];
             const double2 fs = ent[k];
             const double fp = fs.x, sl = fs.y;
@@ -1078,7 +1110,9 @@ __global__ void __launch_bounds__(kThreads, CT_MINB) remap_kernel(RemapArgs a) {
     if (SIO::kU8) fill_decode(sh.dec_d, sh.dec_f, a.u8_as_f32);
     if (threadIdx.x >= 32 && threadIdx.x < 35) {
         const double *tail = lut + 9 * CT_IDT_EDGE_STRIDE(bins) + 4 * (threadIdx.x - 32);
-        sh.grid[threadIdx.x - 32] = AxisGrid{tail[0], tail[1], tail[2], tail[3]};
+        const AxisGrid g{tail[0], tail[1], tail[2], tail[3]};
+        sh.grid[threadIdx.x - 32] = g;
+        sh.amb[threadIdx.x - 32] = remap_ambiguity(g, bins);
     }
     for (int i = threadIdx.x; i < 9 * CT_IDT_EDGE_STRIDE(bins); i += kThreads) sm_tab[i] = lut[i];
     __syncthreads();
