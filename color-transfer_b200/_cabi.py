@@ -93,6 +93,7 @@ SIGNATURES = {
     "ct_psnr": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.c_int64, ctypes.POINTER(ctypes.c_double)]),
     "ct_ssim": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                ctypes.POINTER(ctypes.c_double)]),
+    "ct_distort": (ctypes.c_int, [_P, _BP, _P, ctypes.c_int32, _BP]),
 }
 
 _lib = None

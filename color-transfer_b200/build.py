@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libct_b200.so")
-SOURCES = ["ct_api.cu", "ct_linear.cu", "ct_idt.cu", "ct_u8.cu", "ct_regrain.cu", "ct_metrics.cu"]
+SOURCES = ["ct_api.cu", "ct_linear.cu", "ct_idt.cu", "ct_u8.cu", "ct_regrain.cu", "ct_metrics.cu", "ct_distort.cu"]
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr"]
 

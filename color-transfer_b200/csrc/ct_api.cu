@@ -433,6 +433,11 @@ int ct_psnr(ct_handle h, const float *x, const float *y, int32_t count, int64_t 
     return metric_result(h, result);
 }
 
+int ct_distort(ct_handle h, const ct_batch *src, const ct_distortion *ops, int32_t n_ops, const ct_batch *dst) {
+    CT_ENTER(h);
+    return launch_distort(h, src, ops, n_ops, dst);
+}
+
 int ct_ssim(ct_handle h, const float *x, const float *y, int32_t count, int32_t height, int32_t width,
             int32_t downsample, double *result) {
     CT_ENTER(h);

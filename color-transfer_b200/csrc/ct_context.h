@@ -151,6 +151,9 @@ int launch_apply(ct_context *h, int method, const ct_batch *target, const double
 int launch_u8_to_float(ct_context *h, const uint8_t *in, void *out, int dtype, int64_t n);
 int launch_float_to_u8(ct_context *h, const void *in, int dtype, uint8_t *out, int64_t n);
 
+// ct_distort.cu
+int launch_distort(ct_context *h, const ct_batch *src, const ct_distortion *ops, int n_ops, const ct_batch *dst);
+
 // ct_regrain.cu
 size_t regrain_workspace_bytes(int H, int W);
 int launch_regrain(ct_context *h, const double *in, const double *col, double *out, int H, int W, void *workspace,

@@ -264,6 +264,28 @@ int ct_psnr(ct_handle h, const float *x, const float *y, int32_t count, int64_t 
 int ct_ssim(ct_handle h, const float *x, const float *y, int32_t count, int32_t height, int32_t width,
             int32_t downsample, double *result);
 
+/* ---- artificial-distortion generator ------------------------------
+ * Replaces the torchvision.transforms.functional.adjust_* calls behind ref: utils/data.py:12-22
+ * `setup_grid_distortions` (identity + {brightness, contrast, saturation, hue, gamma} x 6 magnitudes,
+ * applied to the uint8 ground-truth image at ref: utils/data.py:101-104).  One pass over `src`
+ * (CT_U8, device, CT_HWC or CT_CHW) writes every distorted copy: image b * n_ops + k of `dst` (same
+ * dtype / layout / npix, count = src->count * n_ops) is distortion k of image b.  `ops` is HOST memory.
+ * factor: brightness / contrast / saturation factor (>= 0), hue shift in [-0.5, 0.5], gamma (>= 0);
+ * out-of-range factors return CT_E_INVALID (torchvision's ValueError). */
+#define CT_DISTORT_IDENTITY 0
+#define CT_DISTORT_BRIGHTNESS 1
+#define CT_DISTORT_CONTRAST 2
+#define CT_DISTORT_SATURATION 3
+#define CT_DISTORT_HUE 4
+#define CT_DISTORT_GAMMA 5
+#define CT_DISTORT_MAX_OPS 32
+typedef struct ct_distortion {
+    int32_t kind; /* CT_DISTORT_* */
+    int32_t reserved;
+    double factor;
+} ct_distortion;
+int ct_distort(ct_handle h, const ct_batch *src, const ct_distortion *ops, int32_t n_ops, const ct_batch *dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,7 @@ reference by oracle/gen_golden.py), against the reference itself when /root/refe
 present, and sanity of the restated scikit-image Lab conversion."""
 
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -159,3 +160,40 @@ def test_lab_restatement_equals_scikit_image():
     assert np.max(np.abs(rgb2lab(rgb) - skimage_color.rgb2lab(rgb))) < 1e-12
     lab = rgb2lab(rgb)
     assert np.max(np.abs(lab2rgb(lab) - skimage_color.lab2rgb(lab))) < 1e-12
+
+
+# ---- artificial-distortion generator ------------------------------------------
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _distort_close(kind, a, b):
+    d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+    if kind in (2, 5):      # contrast, gamma: at most one level on at most 1 % of the values
+        return d.max() <= 1 and (d == 0).mean() >= 0.99
+    return d.max() == 0
+
+
+def test_distort_oracle_equals_torchvision_golden():
+    """oracle/distort_numpy.py against the outputs torchvision produced (oracle/gen_golden_distort.py)"""
+    from oracle import distort_numpy
+    g = np.load(os.path.join(GOLDEN, "distort_grid.npz"))
+    specs = distort_numpy.grid_specs()
+    assert [k for k, _ in specs] == list(g["kinds"])
+    np.testing.assert_array_equal([f for _, f in specs], g["factors"])
+    for name in ("smooth", "noise", "ramp"):
+        got = distort_numpy.distort_grid(g[f"{name}_image"], specs)
+        for k, (kind, factor) in enumerate(specs):
+            assert _distort_close(kind, got[k], g[f"{name}_grid"][k]), (name, k, kind, factor)
+
+
+def test_distort_oracle_equals_torchvision_live():
+    """the same on fresh random images where torchvision is importable (it is in the build image)"""
+    tvf = pytest.importorskip("torchvision.transforms.functional")
+    import torch
+    from oracle import distort_numpy
+    names = {1: "adjust_brightness", 2: "adjust_contrast", 3: "adjust_saturation", 4: "adjust_hue", 5: "adjust_gamma"}
+    rng = np.random.default_rng(99)
+    img = rng.integers(0, 256, (3, 37, 53), dtype=np.uint8)
+    for kind, factor in distort_numpy.grid_specs()[1:] + [(5, 2.0), (5, 3.0), (1, 0.0), (4, 0.5), (4, -0.5)]:
+        want = getattr(tvf, names[kind])(torch.from_numpy(img), factor).numpy()
+        assert _distort_close(kind, distort_numpy.distort(img, kind, factor), want), (kind, factor)

@@ -9,7 +9,7 @@ files=${@:-ct_idt.cu}
 C=color-transfer_b200/csrc
 mkdir -p tools/scratch/libs/obj_$name
 objs=""
-for f in ct_api ct_linear ct_idt ct_u8 ct_regrain ct_metrics; do
+for f in ct_api ct_linear ct_idt ct_u8 ct_regrain ct_metrics ct_distort; do
   if [[ " $files " == *" $f.cu "* ]]; then
     nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O2 --expt-relaxed-constexpr $defs -c $C/$f.cu -o tools/scratch/libs/obj_$name/$f.o
     objs="$objs tools/scratch/libs/obj_$name/$f.o"
