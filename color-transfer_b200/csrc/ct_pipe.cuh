@@ -14,6 +14,10 @@
 
 #include "ct_common.cuh"
 
+#ifndef CT_PIPE_LAST_REFILLS
+#define CT_PIPE_LAST_REFILLS 1   // 0: thread 0 waits for the stage to be released and refills it (round 1)
+#endif
+
 namespace ct {
 
 constexpr int kTileBytes = kThreads * 48;  // 12 KB for every (dtype, layout)
@@ -31,6 +35,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive, and tell whether this arrival completed the phase (the returned state is the one BEFORE the arrive)
+__device__ __forceinline__ bool mbar_arrive_last(uint32_t bar) {
+    uint64_t state;
+    uint32_t pending;
+    asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(bar) : "memory");
+    asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pending) : "l"(state));
+    return pending == 1u;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -161,7 +173,7 @@ __device__ __forceinline__ void pipe_for_each_group(P &pipe, const typename IO::
     constexpr int G = IO::G;
     constexpr int kTilePx = kThreads * G;
     const int mine = first_tile < ntiles ? (ntiles - first_tile + tile_stride - 1) / tile_stride : 0;
-    auto issue = [&](int i, int s) {  // thread 0 only; s == i % kStages
+    auto issue = [&](int i, int s) {  // one thread; s == i % kStages
         const int64_t p0 = (int64_t)(first_tile + (int64_t)i * tile_stride) * kTilePx;
         const uint32_t dst = pipe.stage + s * kTileBytes, bar = pipe.full + 8 * s;
         mbar_expect_tx(bar, kTileBytes);
@@ -200,11 +212,17 @@ __device__ __forceinline__ void pipe_for_each_group(P &pipe, const typename IO::
             }
         }
         __syncwarp();
+#if CT_PIPE_LAST_REFILLS
+        // this warp has copied its groups out; the warp whose arrival completes the "empty" phase - the last of
+        // the 8 to let go of the stage - refills it at once, so nobody ever waits on that barrier
+        if ((threadIdx.x & 31) == 0 && mbar_arrive_last(empty + (dep & zero)) && i + kStages < mine) issue(i + kStages, s);
+#else
         if ((threadIdx.x & 31) == 0) mbar_arrive(empty + (dep & zero));  // this warp has copied its groups out
         if (threadIdx.x == 0 && i + kStages < mine) {
             mbar_wait(empty, parity);  // all 8 warps are done with the stage
             issue(i + kStages, s);
         }
+#endif
         const int64_t tile0 = (int64_t)(first_tile + (int64_t)i * tile_stride) * kTilePx;
         if constexpr (SPLIT == 1) {
             f(raw[0], tile0);
