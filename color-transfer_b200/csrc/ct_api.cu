@@ -121,7 +121,7 @@ struct IdtLayout {
 static IdtLayout idt_layout(void *base, int64_t npix, int count, int bins, int n_iter) {
     IdtLayout L{};
     Carver c(base);
-    L.plane = (npix + 1) / 2 * 2;
+    L.plane = (npix + 3) / 4 * 4;   // 32-byte aligned planes: K7 writes 256-bit vectors when the source comes in groups of four pixels
     L.state_stride = 3 * L.plane;
     L.state = n_iter >= 2 ? c.take<double>((size_t)count * L.state_stride) : nullptr;
     L.keys = c.take<int64_t>((size_t)count * (n_iter + 1) * CT_IDT_KEYS);

@@ -59,6 +59,13 @@ __device__ __forceinline__ void st_vec(V *p, const V &v) {
 #endif
 }
 
+// 256-bit store (sm_100: STG.E.256) of four doubles to a 32-byte aligned address: a thread that holds four
+// consecutive fp64 values writes whole 32-byte sectors in one instruction (two 128-bit stores at a lane stride
+// of 32 bytes each touch every sector half-filled)
+__device__ __forceinline__ void st_f64x4(double *p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 // decode tables of a uint8 image (shared memory, 256 entries each); unused for float images
 struct Decode {
     const double *d;  // the decoded sample as the kernel's fp64 working value
@@ -202,9 +209,33 @@ struct PixelIO {
     __device__ __forceinline__ static int64_t sub_pixel0(int64_t g, int s) { return g * G + s * GS; }
 
     // store NS pixels starting at pixel p0 (NS is the SOURCE sub-group size; p0 % NS == 0)
+    // wide: float64 destination, 32-byte aligned image (and planes): 256-bit stores where a thread holds 32 contiguous bytes
     template <bool VEC, int NS, typename X>
     __device__ __forceinline__ static void store(T *img, int64_t plane, int64_t p0,
-                                                 const X (&x)[NS][3], bool clamp = false) {
+                                                 const X (&x)[NS][3], bool clamp = false, bool wide = false) {
+        if constexpr (VEC && sizeof(T) == 8 && LAYOUT == CT_CHW && NS == 4) {
+            if (wide) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    st_f64x4(reinterpret_cast<double *>(img) + c * plane + p0, (double)encode(x[0][c], clamp), (double)encode(x[1][c], clamp),
+                             (double)encode(x[2][c], clamp), (double)encode(x[3][c], clamp));
+                return;
+            }
+        }
+        if constexpr (VEC && sizeof(T) == 8 && LAYOUT == CT_HWC && NS == 2) {
+            // 48 contiguous bytes per thread, 32-byte aligned for every other thread: one 256-bit and one 128-bit
+            // store, arranged (without divergence) so that the two lanes that share a sector write it in the
+            // same instruction - three 128-bit stores at a lane stride of 48 bytes touch every sector twice
+            if (wide) {
+                double *o = reinterpret_cast<double *>(img) + 3 * p0;
+                const bool odd = ((p0 >> 1) & 1) != 0;
+                const double e[6] = {(double)encode(x[0][0], clamp), (double)encode(x[0][1], clamp), (double)encode(x[0][2], clamp),
+                                     (double)encode(x[1][0], clamp), (double)encode(x[1][1], clamp), (double)encode(x[1][2], clamp)};
+                st_f64x4(o + (odd ? 2 : 0), odd ? e[2] : e[0], odd ? e[3] : e[1], odd ? e[4] : e[2], odd ? e[5] : e[3]);
+                st_vec(reinterpret_cast<double2 *>(o + (odd ? 0 : 4)), make_double2(odd ? e[0] : e[4], odd ? e[1] : e[5]));
+                return;
+            }
+        }
         if (kU8) {
             // 3 bytes per pixel: NS = 4 -> three 32-bit words (interleaved) or one per plane;
             // NS = 2 (float64 state) -> 16-bit stores

@@ -19,6 +19,9 @@
 #ifndef CT_HIST_COPIES_LOG2
 #define CT_HIST_COPIES_LOG2 3   // lane-interleaved copies of the three histograms for bins <= 256
 #endif
+#ifndef CT_STREAM_ONLY
+#define CT_STREAM_ONLY 0   // 1: K5 / K7 only move their tiles (tools/README.md: how the streaming ceilings in DESIGN.md were measured)
+#endif
 #ifndef CT_HIST_STAGES
 #define CT_HIST_STAGES 3
 #endif
@@ -539,7 +542,7 @@ __device__ void build_lut(const LutArgs &a, int64_t pair, double *sm) {
     for (int j = 0; j < 3; ++j) {
         bool finite;
         const AxisGrid g = grid_from_keys(a.keys + pair * a.keys_stride, j, bins, finite);
-        if (!finite && a.status && threadIdx.x == 0) a.status[pair] = CT_E_NONFINITE;
+        if (!finite && a.status && threadIdx.x == 0 && !CT_STREAM_ONLY) a.status[pair] = CT_E_NONFINITE;
         for (int k = threadIdx.x; k < bins; k += kThreads) {
             const uint64_t ct_ = __ldcg(cnt + (0 * 3 + j) * bins + k);
             const uint64_t cr = __ldcg(cnt + (1 * 3 + j) * bins + k);
@@ -768,6 +771,11 @@ __device__ __forceinline__ void hist_image(const Img &im, int64_t pair, const Sh
         const int ntiles = (int)(im.npix / (kThreads * G));
         pipe_for_each_group<IO>(pipe, base, im.plane_stride, ntiles, first_block, nblocks, zero,
                                 [&](const typename IO::Raw &raw, int64_t) {
+#if CT_STREAM_ONLY   // measurement aid: the tile pipeline alone (what this access pattern can stream), no binning
+                                    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(raw.e);
+                                    if (w32[0] == 0x12345678u && w32[1] == 0x9abcdef0u) count(0, 0);
+                                    return;
+#endif
 #pragma unroll
                                     for (int q = 0; q < IO::NSUB; ++q) {
                                         float xf[GS][3];
@@ -983,6 +991,8 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
     constexpr int G = SIO::G, GS = SIO::GS;
     const Decode dec{sh.dec_d, sh.dec_f};
     const bool clamp = a.clamp != 0, dst_vec = a.dst_vec != 0;
+    // 256-bit stores of a float64 destination (ct_common.cuh: store)
+    const bool wide = dst_vec && (reinterpret_cast<uintptr_t>(dst) & 31) == 0 && (DIO::kLayout == CT_HWC || (a.dst.plane_stride & 3) == 0);
     const int bins = a.bins;
     const int E = CT_IDT_EDGE_STRIDE(bins);
     double r[9], rn[9], lo[3], inv[3];
@@ -999,6 +1009,10 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
         amb[j] = sh.amb[j];
     }
     auto one = [&](const double(&x)[3], double(&y)[3]) {
+#if CT_STREAM_ONLY   // measurement aid: read the state, write it back (what this access pattern can stream)
+        y[0] = x[0]; y[1] = x[1]; y[2] = x[2];
+        return;
+#endif
         double d[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -1046,7 +1060,7 @@ __device__ __forceinline__ void remap_image(const RemapArgs &a, int64_t pair, co
                                          SIO::unpack_sub(raw, q, dec, x);
 #pragma unroll
                                          for (int i = 0; i < GS; ++i) one(x[i], y[i]);
-                                         if (dst_vec) DIO::template store<true, GS>(dst, a.dst.plane_stride, pipe_sub_pixel0<SIO>(tile0, q), y, clamp);
+                                         if (dst_vec) DIO::template store<true, GS>(dst, a.dst.plane_stride, pipe_sub_pixel0<SIO>(tile0, q), y, clamp, wide);
                                          else DIO::template store<false, GS>(dst, a.dst.plane_stride, pipe_sub_pixel0<SIO>(tile0, q), y, clamp);
                                      }
                                  });

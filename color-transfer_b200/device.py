@@ -149,7 +149,7 @@ class IdtStages:
         self.counts = torch.zeros((b, 2, 3, bins), dtype=torch.int64, device=dev)
         self.lut_buf = torch.empty((b, _cabi.lut_doubles(bins)), dtype=torch.float64, device=dev)
         self.status = torch.zeros((b,), dtype=torch.int32, device=dev)
-        self.plane = (self.npix + 1) // 2 * 2
+        self.plane = (self.npix + 3) // 4 * 4     # 32-byte aligned planes (256-bit state stores)
         self.state = torch.empty((b, 3, self.plane), dtype=torch.float64, device=dev) if n_iter >= 2 else None
         self.out = torch.empty(self.t.shape, dtype=torch.float64, device=dev)
         self.tb, self._k1 = batch_of(self.t, _in_flags(self.t, as_float32))
