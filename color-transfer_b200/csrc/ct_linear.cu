@@ -307,6 +307,8 @@ __global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_APPLY_CTAS_PER_SM : CT_
     constexpr int G = SIO::G, GS = SIO::GS;
     const int64_t ngroups = a.src.npix / G;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
+    // 256-bit stores of a 32-byte aligned destination (ct_common.cuh: store)
+    const bool wide = VEC && (reinterpret_cast<uintptr_t>(dst) & 31) == 0 && (DIO::kLayout == CT_HWC || (a.dst.plane_stride & 3) == 0);
     for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += stride) {
         const typename SIO::Raw raw = SIO::template load_raw<VEC>(src, a.src.plane_stride, (int)g);
 #pragma unroll
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_APPLY_CTAS_PER_SM : CT_
                 SIO::unpack_sub_f(raw, q, dec, xs);
                 if constexpr (GS % 2 == 0 && CT_LAB_PACKED) lab::reinhard_pairs_h<GS, CT_REINHARD_FMA_SEEDS>(fold, xs, ys);
                 else lab::reinhard_group_h<GS, CT_REINHARD_FMA_SEEDS>(fold, xs, ys);
-                DIO::template store<VEC, GS>(dst, a.dst.plane_stride, SIO::sub_pixel0(g, q), ys, clamp);
+                DIO::template store<VEC, GS>(dst, a.dst.plane_stride, SIO::sub_pixel0(g, q), ys, clamp, wide);
             } else {
                 double x[GS][3], y[GS][3];
                 float xs[GS][3];
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, LAB ? CT_LAB_APPLY_CTAS_PER_SM : CT_
                 if (LAB) SIO::unpack_sub_f(raw, q, dec, xs);
 #pragma unroll
                 for (int i = 0; i < GS; ++i) apply_pixel<LAB>(xf, xff, x[i], xs[i], y[i]);
-                DIO::template store<VEC, GS>(dst, a.dst.plane_stride, SIO::sub_pixel0(g, q), y, clamp);
+                DIO::template store<VEC, GS>(dst, a.dst.plane_stride, SIO::sub_pixel0(g, q), y, clamp, wide);
             }
         }
     }
