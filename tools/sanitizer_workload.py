@@ -42,3 +42,17 @@ odd = torch.rand(3, 33, 37, 3, device="cuda", dtype=torch.float64)
 device.idt_transfer(odd, odd.flip(0), rot6[:1, :4].expand(3, 4, 3, 3).contiguous(), 255, 4)
 torch.cuda.synchronize()
 print("round-2 sanitizer workload done")
+# round 2, second session: 256-bit stores (32-byte aligned destinations: float32 pairs -> float64 state / results, the
+# float64 interleaved result of the last iteration), the last-releaser tile refill, the distortion generator
+al32 = torch.rand(2, 64, 96, 3, device="cuda", dtype=torch.float32)
+device.idt_transfer(al32, al32.flip(0), rot6[:, :4].contiguous(), 255, 4)
+device.linear_transfer(_cabi.CT_MKL_MK, al32, al32.flip(0)); device.linear_transfer(_cabi.CT_CCS, al32, al32.flip(0))
+al64 = al32.double()
+device.idt_transfer(al64, al64.flip(0), rot6[:, :4].contiguous(), 255, 4); device.linear_transfer(_cabi.CT_MKL_MK, al64, al64.flip(0))
+from color_transfer_b200 import data
+fns = data.setup_grid_distortions()
+img8 = torch.randint(0, 256, (3, 64, 96), dtype=torch.uint8, device="cuda")
+data.distort_grid(img8, fns); data.distort_grid(img8[:, :33, :37].contiguous(), fns)
+data.distort_grid(torch.stack([img8, img8.flip(1)]), fns[:7])
+torch.cuda.synchronize()
+print("round-2 (second session) sanitizer workload done")
