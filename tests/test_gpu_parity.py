@@ -333,6 +333,30 @@ def test_idt_degenerate_ranges(api):
         assert np.max(np.abs(out[ok] - want[ok]), initial=0.0) < 1e-6, name
 
 
+def test_idt_narrow_range_at_large_offset(api):
+    """Values 1000 + 1e-7 * image: the bin grid is ~1e-10 wide per bin at magnitude 1e3, so none of the fp32 /
+    fixed-point shortcuts can decide anything (K4b flags every pixel, K5's error bound exceeds 1/2, K7's grid is
+    "too narrow for its magnitude") and every sample goes through the exact fp64 rules."""
+    _, it, oracle = api
+    t0, r0 = synthetic_pair(64, 96, 77, np.float64, (48, 80))
+    t, r = 1000.0 + 1e-7 * t0, 1000.0 + 1e-7 * r0
+    np.random.seed(5)
+    want, traces = oracle.idt_instrumented(t, r, n_iter=3)
+    np.random.seed(5)
+    trace = {}
+    out = it.iterative_distribution_transfer(t, r, n_iter=3, trace=trace)
+    assert np.array_equal(trace["lo"][0], traces[0]["lo"]) and np.array_equal(trace["hi"][0], traces[0]["hi"])
+    assert np.array_equal(trace["counts_t"][0], traces[0]["counts_t"])
+    assert np.array_equal(trace["counts_r"][0], traces[0]["counts_r"])
+    assert np.array_equal(trace["lut"][0], traces[0]["lut"])
+    # later iterations: the state differs from the reference's by an ulp of 1e3 (r^T d instead of gesv), which is
+    # 3e-4 of a bin here, so a few samples may change bins; the result still agrees to a small part of the 1e-7 range
+    for k in (1, 2):
+        moved = np.abs(trace["counts_t"][k].astype(np.int64) - traces[k]["counts_t"].astype(np.int64)).sum()
+        assert moved <= 2e-3 * t[..., 0].size * 3, (k, moved)
+    assert np.max(np.abs(out - want)) < 1e-10
+
+
 def test_pair0964_notebook_and_cli_variants(api, pair0964):
     """the notebook's input (target = adjust_hue(0964_L, 0.5), the big colour
     mismatch the demo corrects; uint8 sha256 prefix 5d502d2bf161e98f) as float64, and the CLI's
