@@ -966,11 +966,16 @@ struct RemapShared {
     float dec_f[U8 ? 256 : 1];
 };
 
-// K7 takes the bin of a sample as floor(t~), t~ = (p - lo) * inv rounded to 2^-20, whenever t~ is not within
-// 2^-20 of an integer.  That equals the searchsorted answer against the tabulated edges if the distance between
-// t~ and the position of every edge in t-space is below 2^-20: |t~ - t| <= 3 * 2^-53 * bins + 2^-21 (p - lo, inv
-// and the final rounding) and |edges[k] - (lo + k (hi - lo) / bins)| <= 2^-51 * max(|lo|, |hi|), i.e.
-// 2^-51 * max(|lo|, |hi|) * inv in t-space.  True for every grid whose width is not below ~1e-9 of its magnitude.
+// K7 takes the bin of a sample as floor(t~), t~ = (p - lo) * inv rounded to a multiple of 2^-20, unless t~ is an
+// integer or one step (2^-20) beside one; those samples - about 3 in 2^20 - compare against the tabulated edge
+// as before.  An unflagged t~ is at least 2^-19 away from every integer, so floor(t~) is the searchsorted answer
+// against the tabulated edges as long as t~ and the edges' positions in t-space are together off by less than
+// that: the rounding of t~ contributes 2^-21, the arithmetic of t~ (p - lo, inv, the product) at most
+// 3 * 2^-53 * bins, and the edges, computed as k * step + lo with three roundings, sit within
+// 7 * 2^-53 * max(|lo|, |hi|) of lo + k (hi - lo) / bins, i.e. within 7 * 2^-53 * max(|lo|, |hi|) * inv in t-space.
+// remap_ambiguity() demands 3 * 2^-53 * bins + 2^-51 * max(|lo|, |hi|) * inv < 2^-22, which keeps the total below
+// 2^-21 + 2^-21 - a quarter of the 2^-19 available - and holds for every grid whose width is not below ~1e-9 of
+// its magnitude; otherwise every sample is flagged.
 #ifndef CT_REMAP_FLOOR
 #define CT_REMAP_FLOOR 1
 #endif
