@@ -703,6 +703,12 @@ def rowshard_section(a, ctx):
         ms = timed(lambda: sharded.linear_transfer_sharded(code, tgt, ref, comm=comm, handle=handle), 5)
         res[name] = {"ms_per_pair": ms, "value": npix / 1e6 / (ms / 1e3), "collectives": 1,
                      "frac_of_hbm_aggregate": bpp * npix / (ms / 1e3) / 1e9 / (peak * world)}
+    # what the 8 collectives of one IDT cost by themselves: the two exchanges of an iteration on empty streams
+    keys = torch.zeros(6, dtype=torch.int64, device=dev)
+    counts = torch.zeros(2 * 3 * BINS, dtype=torch.int64, device=dev)
+    us_pair = timed(lambda: (comm.min_(keys), comm.sum_(counts)), 50) * 1e3
+    res["idt"]["collective_us"] = {"min_keys_plus_sum_counts": us_pair, "per_pair_total": us_pair * collectives_idt / 2,
+                                   "note": "NCCL all-reduce MIN of 6 int64 + SUM of 6*bins int64, back to back on an idle stream"}
     res["ms_per_pair"] = res["idt"]["ms_per_pair"]
     res["frac_of_hbm_aggregate"] = res["idt"]["frac_of_hbm_aggregate"]
     res["collectives"] = collectives_idt
